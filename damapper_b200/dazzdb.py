@@ -1,0 +1,120 @@
+"""Minimal DAZZ_DB writer/reader (stub + .idx + .bps) for synthetic workloads.
+
+The DAZZ_DB tools (fasta2DB, fasta2DAM, DBsplit) are not part of the reference tree,
+so databases are written directly in the on-disk layout the reference reads:
+  stub      reference DB.h:431-435 (DB_NFILE/DB_FDATA/DB_NBLOCK/DB_PARAMS/DB_BDATA)
+  .<root>.idx   raw DAZZ_DB (112 B) + DAZZ_READ (40 B) records, reference DB.h:285-295,390-420
+  .<root>.bps   2 bits/base, first base in the top bits, reference DB.c:319-363
+and the in-memory block form of Load_All_Reads (reference DB.c:1389-1441).
+"""
+from __future__ import annotations
+
+import os
+import struct
+
+import numpy as np
+
+DB_HDR = struct.Struct("<iiii4fi4xqiiiii4xqi4xqqq")   # 112 bytes
+DB_READ = struct.Struct("<iii4xqqi4x")                # 40 bytes
+DB_BEST = 0x800
+DB_ALL = 0x1
+assert DB_HDR.size == 112 and DB_READ.size == 40
+
+
+def pack_bps(seq: np.ndarray) -> bytes:
+    """2-bit pack one read; (len+3)>>2 bytes, first base in the two most significant bits."""
+    n = seq.size
+    pad = (-n) % 4
+    s = np.concatenate([seq.astype(np.uint8), np.zeros(pad, dtype=np.uint8)]).reshape(-1, 4)
+    return ((s[:, 0] << 6) | (s[:, 1] << 4) | (s[:, 2] << 2) | s[:, 3]).astype(np.uint8).tobytes()
+
+
+def write_db(path: str, seqs, is_dam: bool = False, nblocks: int = 1, block_bounds=None) -> str:
+    """Write a DB/DAM holding `seqs` (list of uint8 arrays 0..3, or (bases, rlen) tuple).
+
+    `nblocks` splits the reads evenly by count into blocks (or pass explicit
+    `block_bounds` = list of first-read indices, len nblocks+1).  cutoff=0/all=1 so
+    Trim_DB is a no-op (reference DB.c:918).  Returns the stub path."""
+    if isinstance(seqs, tuple):
+        bases, rlen = seqs
+        rlen = np.asarray(rlen, dtype=np.int64)
+        offs = np.concatenate([[0], np.cumsum(rlen)])
+        get = lambda i: bases[offs[i]:offs[i + 1]]
+        n = rlen.size
+    else:
+        n = len(seqs)
+        rlen = np.array([s.size for s in seqs], dtype=np.int64)
+        get = lambda i: seqs[i]
+    d, base = os.path.split(path)
+    d = d or "."
+    root = base
+    for ext in (".dam", ".db"):
+        if root.endswith(ext):
+            root = root[: -len(ext)]
+    ext = ".dam" if is_dam else ".db"
+    stub = os.path.join(d, root + ext)
+    if block_bounds is None:
+        block_bounds = [int(n * i / nblocks) for i in range(nblocks + 1)]
+    nblocks = len(block_bounds) - 1
+
+    # .bps (vectorised when all reads are the packed tuple form)
+    bps_path = os.path.join(d, "." + root + ".bps")
+    boff = np.zeros(n, dtype=np.int64)
+    with open(bps_path, "wb") as f:
+        o = 0
+        for i in range(n):
+            b = pack_bps(get(i))
+            boff[i] = o
+            f.write(b)
+            o += len(b)
+
+    allb = np.concatenate([get(i) for i in range(n)]) if n else np.zeros(0, np.uint8)
+    cnt = np.bincount(allb, minlength=4).astype(np.float64)
+    freq = cnt / max(1.0, cnt.sum())
+    totlen = int(rlen.sum())
+    maxlen = int(rlen.max()) if n else 0
+    with open(os.path.join(d, "." + root + ".idx"), "wb") as f:
+        f.write(DB_HDR.pack(n, n, 0, DB_ALL, float(freq[0]), float(freq[1]), float(freq[2]),
+                            float(freq[3]), maxlen, totlen, n, 0, 0, 0, 0, 0, 0, 0, 0, 0))
+        for i in range(n):
+            f.write(DB_READ.pack(i if is_dam else i, int(rlen[i]), 0, int(boff[i]), 0, DB_BEST))
+
+    with open(stub, "w") as f:
+        f.write("files = %9d\n" % 1)
+        f.write("  %9d %s %s\n" % (n, root, root))
+        f.write("blocks = %9d\n" % nblocks)
+        f.write("size = %11d cutoff = %9d all = %1d\n" % (max(1, totlen // 1000000 + 1), 0, 1))
+        for b in block_bounds:
+            f.write(" %9d %9d\n" % (b, b))
+    return stub
+
+
+def load_block(seqs) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """In-memory block image as produced by Load_All_Reads (reference DB.c:1389-1441).
+
+    Returns (bases, boff, rlen): `bases` is one byte per base with a 4 before the first
+    read and after every read (bases[0] is the leading 4; read i starts at bases[1+boff[i]]),
+    `boff` has nreads+1 entries."""
+    if isinstance(seqs, tuple):
+        b, rlen = seqs
+        rlen = np.asarray(rlen, dtype=np.int64)
+        n = rlen.size
+        boff = np.concatenate([[0], np.cumsum(rlen + 1)]).astype(np.int64)
+        out = np.full(int(boff[-1]) + 4, 4, dtype=np.uint8)
+        src_off = np.concatenate([[0], np.cumsum(rlen)])
+        idx = np.arange(int(rlen.sum()), dtype=np.int64)
+        rid = np.repeat(np.arange(n, dtype=np.int64), rlen)
+        out[1 + boff[rid] + (idx - src_off[rid])] = b
+        return out, boff, rlen.astype(np.int32)
+    n = len(seqs)
+    rlen = np.array([s.size for s in seqs], dtype=np.int64)
+    boff = np.concatenate([[0], np.cumsum(rlen + 1)]).astype(np.int64)
+    out = np.full(int(boff[-1]) + 4, 4, dtype=np.uint8)
+    for i, s in enumerate(seqs):
+        out[1 + boff[i]: 1 + boff[i] + s.size] = s
+    return out, boff, rlen.astype(np.int32)
+
+
+def revcomp_contigs(contigs):
+    """complement_DB (reference damapper.c:433-525): reverse-complement every contig in place."""
+    return [(3 - c[::-1]).astype(np.uint8) for c in contigs]
