@@ -1,0 +1,38 @@
+// Device-resident DB block and k-mer index (internal).
+#pragma once
+#include <vector>
+#include "common.cuh"
+
+namespace damgpu {
+
+// Device image of a loaded DB block (Load_All_Reads, DB.c:1389-1441): bases[-1] == 4, read i at
+// bases[boff[i] .. boff[i]+rlen[i]) followed by a 4.
+struct DeviceBlock
+{ uint8_t *raw = nullptr;       // allocation
+  uint8_t *bases = nullptr;     // raw+16, 16-byte aligned
+  int64_t *boff = nullptr;      // nreads+1
+  int32_t *rlen = nullptr;
+  int      nreads = 0, tfirst = 0, maxlen = 0;
+  int64_t  totlen = 0, total = 0, sizeof_db = 0;
+  std::vector<int64_t> h_boff;
+  std::vector<int32_t> h_rlen;
+};
+
+// Result of Sort_Kmers: len records + the 2 sentinels (map.c:772-773), on the device.
+struct KmerIndex
+{ KmerPos *list = nullptr;
+  int      len = 0;
+  float    ms_extract = 0.f, ms_sort = 0.f;
+  int      npass = 0;
+};
+
+DeviceBlock *upload_block(const uint8_t *bases, const int64_t *boff, const int32_t *rlen,
+                          int nreads, int tfirst, int maxlen, int64_t totlen, int64_t sizeof_db,
+                          cudaStream_t stream);
+void         free_block(DeviceBlock *blk);
+// complement_DB(block, inplace) of the reference driver (damapper.c:433-469), on the device
+void         complement_block(DeviceBlock *blk, cudaStream_t stream);
+KmerIndex   *sort_kmers(const DeviceBlock *blk, int K, int suppress, cudaStream_t stream);
+void         free_index(KmerIndex *idx);
+
+}  // namespace damgpu

@@ -1,0 +1,121 @@
+/* libdamgpu -- C ABI of the B200-native DAMAPPER mapping core.
+ *
+ * The library replaces everything behind the reference's map.h seam (reference map.h:16-39):
+ * Set_Filter_Params, Sort_Kmers, Match_Filter and Reporter, with all compute in sm_100a CUDA
+ * kernels.  There is no CPU fallback: every entry point fails through the fatal callback
+ * (the reference's Clean_Exit, map.h:39) when no CUDA device is usable.
+ *
+ * Two layers are exported:
+ *   1. damgpu_Set_Filter_Params / damgpu_Sort_Kmers / damgpu_Match_Filter / damgpu_Reporter
+ *      mirror the four map.h functions call for call (same argument order and meaning), taking a
+ *      plain-C view of the DAZZ_DB fields the core reads (damgpu_block) instead of DAZZ_DB*.
+ *   2. handle-based entry points (damgpu_block_*, damgpu_index_*, damgpu_seeds_*, ...) that keep
+ *      blocks and indices resident in HBM between calls; layer 1 is written on top of them and
+ *      the parity tests use them to compare every intermediate array with the oracle.
+ *
+ * All functions are called from one host thread (the reference's core is non-reentrant as
+ * well: file-scope statics, map.c:164-171,453-455,867-870,1011-1017,2885).
+ */
+#ifndef LIBDAMGPU_H
+#define LIBDAMGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* KmerPos / SeedPair, reference map.c:78-89 (little-endian layout) */
+typedef struct { uint64_t code; int32_t rpos; int32_t read; } damgpu_kmer;
+typedef struct { int32_t diag, apos, bread, aread; } damgpu_seed;
+
+/* The fields of a loaded DAZZ_DB block that the core reads (reference DB.h:390-420 and
+ * Load_All_Reads DB.c:1389-1441): bases[-1] == 4, read i occupies
+ * bases[boff[i] .. boff[i]+rlen[i]) and is followed by a 4; boff has nreads+1 entries
+ * (DAZZ_READ.boff), rlen nreads entries (DAZZ_READ.rlen). */
+typedef struct {
+  const uint8_t *bases;
+  const int64_t *boff;
+  const int32_t *rlen;
+  int32_t  nreads;
+  int32_t  tfirst;          /* DAZZ_DB.tfirst */
+  int32_t  maxlen;          /* DAZZ_DB.maxlen */
+  int64_t  totlen;          /* DAZZ_DB.totlen */
+  int64_t  sizeof_db;       /* sizeof_DB(block), DB.c:1044 -- enters the k-mer hit cap */
+} damgpu_block;
+
+/* The globals map.h:16-23 declares extern and damapper.c:58-65 defines. */
+typedef struct {
+  int32_t     verbose;      /* VERBOSE  */
+  int32_t     profile;      /* PROFILE  (-p) */
+  int32_t     spacing;      /* SPACING  (-s) */
+  double      best_tie;     /* BEST_TIE (-n) */
+  const char *sort_path;    /* SORT_PATH */
+  uint64_t    mem_limit;    /* MEM_LIMIT, bytes; 0 = no cap (-M0) */
+  uint64_t    mem_physical; /* MEM_PHYSICAL */
+} damgpu_options;
+
+/* What New_Align_Spec(ave_corr, spacing, freq, reach=1) is given (align.c:222, damapper.c:796).
+ * The opaque Align_Spec cannot cross the ABI, the library rebuilds the tables itself. */
+typedef struct {
+  double  ave_corr;         /* -e */
+  int32_t trace_space;      /* -s */
+  float   freq[4];          /* base frequencies of the reference DB */
+} damgpu_align_spec;
+
+typedef struct damgpu_dblock damgpu_dblock;   /* a DB block resident in HBM      */
+typedef struct damgpu_index  damgpu_index;    /* a sorted k-mer list in HBM      */
+typedef struct damgpu_seeds  damgpu_seeds;    /* sorted seed hits in HBM         */
+
+/* ---- library ------------------------------------------------------------------------ */
+int  damgpu_init(int device);                         /* 0 = ok, else no usable CUDA device */
+void damgpu_set_options(const damgpu_options *opts);
+void damgpu_set_fatal(void (*clean_exit)(int));       /* Clean_Exit, map.h:39 / damapper.c:543 */
+const char *damgpu_last_error(void);
+uint64_t damgpu_launch_count(void);                   /* kernels launched so far            */
+void damgpu_time_kernels(int on);                     /* record per-phase CUDA-event times  */
+/* ms of the last Sort_Kmers: [0]=extraction kernel, [1]=all radix passes, [2]=#passes */
+void damgpu_last_sort_times(float out[3]);
+
+/* ---- layer 1: the map.h quartet ------------------------------------------------------- */
+/* Set_Filter_Params, map.h:25 / map.c:124-150.  Returns 1 if kmer <= 1. */
+int   damgpu_Set_Filter_Params(int kmer, int suppress, int nthreads);
+/* Sort_Kmers, map.h:27 / map.c:655-822.  Returns an opaque handle (NULL and *len = 0 when the
+ * block has no k-mers).  Release with damgpu_index_free (replaces free(), damapper.c:879). */
+void *damgpu_Sort_Kmers(const damgpu_block *block, int *len);
+/* Match_Filter, map.h:29-30 / map.c:2889-3209.  ablock/atable = reads, bblock/btable =
+ * reference block (consumed: btable is released, as the reference frees it, map.c:3181-3182). */
+void  damgpu_Match_Filter(const damgpu_block *ablock, const damgpu_block *bblock,
+                          void *atable, int alen, void *btable, int blen, int comp, int start);
+/* Reporter, map.h:35-36 / map.c:3227-3319.  mflag: bit0 FLAG_DOA, bit1 FLAG_DOB. */
+void  damgpu_Reporter(const char *aname, const damgpu_block *ablock, const char *bname,
+                      const damgpu_block *bblock, const damgpu_align_spec *spec, int mflag);
+
+/* ---- layer 2: resident handles -------------------------------------------------------- */
+damgpu_dblock *damgpu_block_upload(const damgpu_block *block);
+void           damgpu_block_free(damgpu_dblock *blk);
+/* complement_DB(block, inplace=1), damapper.c:433-469, on the device */
+void           damgpu_block_complement(damgpu_dblock *blk);
+void           damgpu_block_download_bases(const damgpu_dblock *blk, uint8_t *bases);
+
+damgpu_index  *damgpu_index_build(const damgpu_dblock *blk);               /* Sort_Kmers */
+int            damgpu_index_len(const damgpu_index *idx);
+void           damgpu_index_download(const damgpu_index *idx, damgpu_kmer *out); /* len+2 recs */
+void           damgpu_index_free(damgpu_index *idx);
+/* raw device pointer of the list (len+2 records), for NCCL broadcast by the caller */
+void          *damgpu_index_device_ptr(const damgpu_index *idx);
+damgpu_index  *damgpu_index_adopt(void *device_list, int len);             /* takes ownership */
+
+/* merge-join + seed sort of Match_Filter (map.c:2958-3126) as a separate stage */
+damgpu_seeds  *damgpu_seeds_build(const damgpu_index *reads_idx, const damgpu_dblock *reads,
+                                  const damgpu_index *ref_idx, const damgpu_dblock *ref);
+int64_t        damgpu_seeds_count(const damgpu_seeds *s);
+int            damgpu_seeds_limit(const damgpu_seeds *s);
+void           damgpu_seeds_histogram(const damgpu_seeds *s, int64_t *histo /*[10000]*/);
+void           damgpu_seeds_download(const damgpu_seeds *s, damgpu_seed *out); /* count+1 recs */
+void           damgpu_seeds_free(damgpu_seeds *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
