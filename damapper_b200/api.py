@@ -64,6 +64,28 @@ SYMBOLS = {
     "damgpu_seeds_histogram": (None, [_P, _P]),
     "damgpu_seeds_download": (None, [_P, _P]),
     "damgpu_seeds_free": (None, [_P]),
+    "damgpu_Match_Filter": (None, [C.POINTER(CBlock), C.POINTER(CBlock), _P, C.c_int, _P, C.c_int,
+                                   C.c_int, C.c_int]),
+    "damgpu_Reporter": (None, [C.c_char_p, C.POINTER(CBlock), C.c_char_p, C.POINTER(CBlock),
+                               C.POINTER(CAlignSpec), C.c_int]),
+    "damgpu_mapper_new": (_P, [_P, _P]),
+    "damgpu_mapper_free": (None, [_P]),
+    "damgpu_mapper_match": (None, [_P, _P, _P, C.c_int, C.c_int]),
+    "damgpu_mapper_chain": (None, [_P, _P, C.c_int, C.c_int, C.c_int]),
+    "damgpu_mapper_last_hits": (C.c_int64, [_P]),
+    "damgpu_mapper_num_candidates": (C.c_int64, [_P]),
+    "damgpu_mapper_get_candidates": (C.c_int64, [_P, _P, _P, _P, C.c_int64]),
+    "damgpu_mapper_get_cover": (C.c_int64, [_P, _P, C.c_int64]),
+    "damgpu_mapper_report": (_P, [_P, _P, C.POINTER(CAlignSpec), C.c_int]),
+    "damgpu_report_free": (None, [_P]),
+    "damgpu_report_bytes": (C.c_int64, [_P, C.c_int]),
+    "damgpu_report_records": (C.c_int64, [_P, C.c_int]),
+    "damgpu_report_copy": (None, [_P, C.c_int, _P]),
+    "damgpu_report_stats": (None, [_P, C.POINTER(C.c_int64)]),
+    "damgpu_report_write_las": (C.c_int, [_P, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p,
+                                          C.c_int, C.c_int]),
+    "damgpu_report_write_profile": (C.c_int, [_P, C.POINTER(CBlock), C.c_char_p, C.c_char_p,
+                                              C.c_int]),
 }
 
 _lib = None
@@ -209,3 +231,129 @@ def last_sort_times():
     v = (C.c_float * 3)()
     load().damgpu_last_sort_times(v)
     return dict(extract_ms=v[0], sort_ms=v[1], npass=int(v[2]))
+
+
+class Report:
+    def __init__(self, handle):
+        self.h = handle
+
+    def _bytes(self, fam):
+        n = load().damgpu_report_bytes(self.h, fam)
+        buf = np.zeros(max(n, 1), dtype=np.uint8)
+        load().damgpu_report_copy(self.h, fam, buf.ctypes.data)
+        return buf[:n].tobytes()
+
+    @property
+    def a(self):
+        return self._bytes(0)
+
+    @property
+    def b(self):
+        return self._bytes(1)
+
+    @property
+    def prof(self):
+        return self._bytes(2)
+
+    def records(self, fam=0):
+        return load().damgpu_report_records(self.h, fam)
+
+    def stats(self):
+        v = (C.c_int64 * 8)()
+        load().damgpu_report_stats(self.h, v)
+        return dict(nalign=v[0], nwaves=v[1], ncells=v[2], h2=v[3], overflow_jobs=v[4],
+                    empty_band=v[5], align_ms=v[6] / 1000.0)
+
+    def write_las(self, fam, directory, aname, bname, nfiles, tspace):
+        rc = load().damgpu_report_write_las(self.h, fam, directory.encode(), aname.encode(),
+                                            bname.encode(), nfiles, tspace)
+        if rc != 0:
+            raise IOError("cannot write .las files in %s" % directory)
+
+    def free(self):
+        if self.h:
+            load().damgpu_report_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.free()
+
+
+class Mapper:
+    """Per-reads-block state between Match_Filter calls and Reporter (map.c:2885)."""
+
+    def __init__(self, reads: DeviceBlock, ridx: Index):
+        self.reads, self.ridx = reads, ridx
+        self.h = load().damgpu_mapper_new(reads.h, ridx.h)
+
+    def match(self, ref: DeviceBlock, gidx: Index, comp: int, start: int):
+        load().damgpu_mapper_match(self.h, ref.h, gidx.h, comp, start)
+
+    def chain(self, seeds: Seeds, bstart: int, comp: int, start: int):
+        load().damgpu_mapper_chain(self.h, seeds.h, bstart, comp, start)
+
+    @property
+    def last_hits(self):
+        return load().damgpu_mapper_last_hits(self.h)
+
+    def candidates(self):
+        L = load()
+        n = L.damgpu_mapper_num_candidates(self.h)
+        out = np.zeros(n, dtype=CAND_DT)
+        jcnt = np.zeros(n, dtype=np.int32)
+        nj = L.damgpu_mapper_get_candidates(self.h, out.ctypes.data, jcnt.ctypes.data, None, 0)
+        jumps = np.zeros((max(nj, 1), 2), dtype=np.int32)
+        L.damgpu_mapper_get_candidates(self.h, out.ctypes.data, jcnt.ctypes.data, jumps.ctypes.data, nj)
+        return out, jcnt, jumps[:nj]
+
+    def cover(self):
+        n = load().damgpu_mapper_get_cover(self.h, None, 0)
+        out = np.zeros(n, dtype=np.int16)
+        load().damgpu_mapper_get_cover(self.h, out.ctypes.data, n)
+        return out
+
+    def report(self, wholeref: DeviceBlock, ave_corr=0.85, spacing=100,
+               freq=(.25, .25, .25, .25), mflag=1) -> Report:
+        spec = CAlignSpec(ave_corr, spacing, (C.c_float * 4)(*freq))
+        return Report(load().damgpu_mapper_report(self.h, wholeref.h, C.byref(spec), mflag))
+
+    def free(self):
+        if self.h:
+            load().damgpu_mapper_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.free()
+
+
+def map_block(reads: HostBlock, ref_blocks, wholeref: HostBlock, kmer=20, suppress=0, spacing=100,
+              profile=0, ave_corr=0.85, best_tie=1.0, freq=(.25, .25, .25, .25),
+              mem_limit=64 << 30, do_a=1, do_b=0, nthreads=4, want_candidates=False):
+    """The damapper flow for one reads block (damapper.c:825-879) on the GPU: index the reads,
+    then for every reference block Match_Filter forward and complemented (the block is
+    complemented on the device), then Reporter against the whole reference.
+    `ref_blocks` is a list of forward HostBlocks.  Returns a dict like oracle.map_block."""
+    init()
+    set_filter_params(kmer, suppress, nthreads)
+    set_options(profile=profile, spacing=spacing, best_tie=best_tie, mem_limit=mem_limit)
+    dr = DeviceBlock(reads)
+    ir = Index(dr)
+    m = Mapper(dr, ir)
+    for k, fwd in enumerate(ref_blocks):
+        dg = DeviceBlock(fwd)
+        ig = Index(dg)
+        m.match(dg, ig, 0, 1 if k == 0 else 0)
+        ig.free()
+        dg.complement()
+        ig = Index(dg)
+        m.match(dg, ig, 1, 0)
+        ig.free()
+        dg.free()
+    cands = m.candidates() if want_candidates else None
+    cover = m.cover() if (want_candidates and profile) else None
+    dw = DeviceBlock(wholeref)
+    rep = m.report(dw, ave_corr, spacing, freq, (1 if do_a else 0) | (2 if do_b else 0))
+    out = dict(a=rep.a, anrec=rep.records(0), b=rep.b, bnrec=rep.records(1), prof=rep.prof,
+               stats=rep.stats(), candidates=cands, cover=cover)
+    rep.free(); dw.free(); m.free(); ir.free(); dr.free()
+    return out

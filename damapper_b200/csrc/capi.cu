@@ -1,12 +1,15 @@
 // C ABI of libdamgpu (include/libdamgpu.h): thin extern "C" layer over the CUDA stages.
 #include <stdarg.h>
 #include <string.h>
+#include <math.h>
 #include <string>
 #include "../../include/libdamgpu.h"
 #include "common.cuh"
 #include "index.cuh"
 #include "seeds.cuh"
 #include "mapper.cuh"
+#include "report.cuh"
+#include <vector>
 
 namespace damgpu {
 
@@ -180,19 +183,263 @@ void damgpu_seeds_download(const damgpu_seeds *s, damgpu_seed *out)
 
 void damgpu_seeds_free(damgpu_seeds *s) { free_seeds(reinterpret_cast<SeedSet *>(s)); }
 
+// ---- mapper -------------------------------------------------------------------------------
+
+struct MapperH { Mapper *m; const KmerIndex *ridx; };
+
+damgpu_mapper *damgpu_mapper_new(const damgpu_dblock *reads, const damgpu_index *reads_idx)
+{ need_gpu();
+  MapperH *h = new MapperH();
+  h->m = mapper_new(reinterpret_cast<const DeviceBlock *>(reads));
+  h->ridx = reinterpret_cast<const KmerIndex *>(reads_idx);
+  return reinterpret_cast<damgpu_mapper *>(h);
+}
+
+void damgpu_mapper_free(damgpu_mapper *mm)
+{ MapperH *h = reinterpret_cast<MapperH *>(mm);
+  if (h == nullptr) return;
+  mapper_free(h->m);
+  delete h;
+}
+
+void damgpu_mapper_chain(damgpu_mapper *mm, const damgpu_seeds *s, int bstart, int comp, int start)
+{ MapperH *h = reinterpret_cast<MapperH *>(mm);
+  if (start) mapper_reset(h->m);
+  chain_seeds(h->m, reinterpret_cast<const SeedSet *>(s), bstart, comp, 0);
+}
+
+void damgpu_mapper_match(damgpu_mapper *mm, const damgpu_dblock *ref, const damgpu_index *ref_idx,
+                         int comp, int start)
+{ MapperH *h = reinterpret_cast<MapperH *>(mm);
+  const DeviceBlock *rb = reinterpret_cast<const DeviceBlock *>(ref);
+  const KmerIndex *gi = reinterpret_cast<const KmerIndex *>(ref_idx);
+  h->m->last_nhits = 0;
+  if (h->ridx == nullptr || h->ridx->len == 0 || gi == nullptr || gi->len == 0)   // map.c:2955-2956
+    return;
+  SeedSet *ss = merge_join(h->ridx, h->m->reads, gi, rb, g_par.kmer, g_par.mem_limit, 0);
+  h->m->last_nhits = ss->nhits; h->m->last_limit = ss->limit;
+  if (g_par.verbose)
+    { printf("\n   Capping mutual k-mer matches over %d (effectively -t%d)\n", ss->limit,
+             (int) sqrt(1. * ss->limit));
+      printf("   Hit count = %lld\n", (long long) ss->nhits);
+      fflush(stdout);
+    }
+  if (start) mapper_reset(h->m);
+  chain_seeds(h->m, ss, rb->tfirst, comp, 0);
+  free_seeds(ss);
+}
+
+int64_t damgpu_mapper_last_hits(const damgpu_mapper *mm)
+{ return reinterpret_cast<const MapperH *>(mm)->m->last_nhits; }
+
+// host copies of the candidate pool, walked per read (newest first, as the lists are linked)
+static void fetch_pool(const Mapper *m, std::vector<Candidate> &cand, std::vector<int> &head,
+                       std::vector<uint32_t> &jumps)
+{ int ctop = 0; unsigned long long jtop = 0;
+  CUDA_CHECK(cudaMemcpy(&ctop, m->cand_top, sizeof(int), cudaMemcpyDeviceToHost));
+  CUDA_CHECK(cudaMemcpy(&jtop, m->jump_top, sizeof(jtop), cudaMemcpyDeviceToHost));
+  cand.resize(ctop); head.resize(m->reads->nreads); jumps.resize(jtop);
+  if (ctop) CUDA_CHECK(cudaMemcpy(cand.data(), m->cand, sizeof(Candidate) * ctop, cudaMemcpyDeviceToHost));
+  if (jtop) CUDA_CHECK(cudaMemcpy(jumps.data(), m->jumps, sizeof(uint32_t) * jtop, cudaMemcpyDeviceToHost));
+  CUDA_CHECK(cudaMemcpy(head.data(), m->head, sizeof(int) * head.size(), cudaMemcpyDeviceToHost));
+}
+
+int64_t damgpu_mapper_num_candidates(const damgpu_mapper *mm)
+{ const Mapper *m = reinterpret_cast<const MapperH *>(mm)->m;
+  std::vector<Candidate> cand; std::vector<int> head; std::vector<uint32_t> jumps;
+  fetch_pool(m, cand, head, jumps);
+  int64_t n = 0;
+  for (size_t r = 0; r < head.size(); r++)
+    for (int c = head[r]; c >= 0; c = cand[c].next) n++;
+  return n;
+}
+
+int64_t damgpu_mapper_get_candidates(const damgpu_mapper *mm, damgpu_candidate *out, int32_t *jcnt,
+                                     int32_t *jout, int64_t jmax)
+{ const Mapper *m = reinterpret_cast<const MapperH *>(mm)->m;
+  std::vector<Candidate> cand; std::vector<int> head; std::vector<uint32_t> jumps;
+  fetch_pool(m, cand, head, jumps);
+  int64_t n = 0, nj = 0;
+  for (size_t r = 0; r < head.size(); r++)
+    for (int c = head[r]; c >= 0; c = cand[c].next)
+      { const Candidate &C = cand[c];
+        if (out)
+          { damgpu_candidate &o = out[n];
+            o.read = (int) r; o.score = C.score; o.length = C.length; o.bread = C.bread; o.comp = C.comp;
+            o.afirst = C.afirst; o.alast = C.alast; o.bfirst = C.bfirst; o.blast = C.blast;
+          }
+        if (jcnt) jcnt[n] = C.length;
+        for (int k = 0; k < C.length; k++)
+          { if (jout && nj < jmax)
+              { const uint32_t j = jumps[C.chain + k];
+                jout[2 * nj] = (int32_t) (j & 0xffff); jout[2 * nj + 1] = (int32_t) (j >> 16);
+              }
+            nj++;
+          }
+        n++;
+      }
+  return nj;
+}
+
+int64_t damgpu_mapper_get_cover(const damgpu_mapper *mm, int16_t *out, int64_t max)
+{ const Mapper *m = reinterpret_cast<const MapperH *>(mm)->m;
+  const int64_t tot = m->h_coff[m->reads->nreads];
+  if (out != nullptr)
+    CUDA_CHECK(cudaMemcpy(out, m->cover, sizeof(int16_t) * (size_t) (tot < max ? tot : max),
+                          cudaMemcpyDeviceToHost));
+  return tot;
+}
+
+damgpu_report *damgpu_mapper_report(damgpu_mapper *mm, const damgpu_dblock *wholeref,
+                                    const damgpu_align_spec *spec, int mflag)
+{ MapperH *h = reinterpret_cast<MapperH *>(mm);
+  if (spec->trace_space != g_par.spacing)
+    fatal("Reporter: align spec trace spacing %d differs from SPACING %d", spec->trace_space,
+          g_par.spacing);
+  ReportOut *r = reporter(h->m, reinterpret_cast<const DeviceBlock *>(wholeref), spec->ave_corr,
+                          spec->freq, (mflag & 1) != 0, (mflag & 2) != 0, 0);
+  return reinterpret_cast<damgpu_report *>(r);
+}
+
+void damgpu_report_free(damgpu_report *r) { delete reinterpret_cast<ReportOut *>(r); }
+
+int64_t damgpu_report_bytes(const damgpu_report *rr, int family)
+{ const ReportOut *r = reinterpret_cast<const ReportOut *>(rr);
+  return family == 0 ? (int64_t) r->a.size() : family == 1 ? (int64_t) r->b.size() : (int64_t) r->prof.size();
+}
+
+int64_t damgpu_report_records(const damgpu_report *rr, int family)
+{ const ReportOut *r = reinterpret_cast<const ReportOut *>(rr);
+  return family == 0 ? r->nrec_a : family == 1 ? r->nrec_b : 0;
+}
+
+void damgpu_report_copy(const damgpu_report *rr, int family, uint8_t *out)
+{ const ReportOut *r = reinterpret_cast<const ReportOut *>(rr);
+  const std::vector<uint8_t> &v = family == 0 ? r->a : family == 1 ? r->b : r->prof;
+  if (!v.empty()) memcpy(out, v.data(), v.size());
+}
+
+void damgpu_report_stats(const damgpu_report *rr, int64_t out[8])
+{ const ReportOut *r = reinterpret_cast<const ReportOut *>(rr);
+  out[0] = r->nalign; out[1] = r->nwaves; out[2] = r->ncells; out[3] = r->h2_events;
+  out[4] = r->overflow_jobs; out[5] = r->empty_band; out[6] = (int64_t) (r->ms_align * 1000.f); out[7] = 0;
+}
+
+// per-"thread" files: reads [ (i*n)>>shift, ((i+1)*n)>>shift ), map.c:3148,3250-3261,2421-2428
+int damgpu_report_write_las(const damgpu_report *rr, int family, const char *dir, const char *aname,
+                            const char *bname, int nfiles, int tspace)
+{ const ReportOut *r = reinterpret_cast<const ReportOut *>(rr);
+  const std::vector<uint8_t> &v = family == 0 ? r->a : r->b;
+  const std::vector<int64_t> &off = family == 0 ? r->read_off_a : r->read_off_b;
+  const std::vector<int> &nrec = family == 0 ? r->read_nrec_a : r->read_nrec_b;
+  if (off.empty()) return 1;
+  const int64_t n = (int64_t) off.size() - 1;
+  int shift = 0;
+  while ((2 << shift) <= nfiles) shift++;
+  const int nf = 1 << shift;
+  for (int i = 0; i < nf; i++)
+    { const int64_t r0 = (i * n) >> shift, r1 = (i == nf - 1) ? n : (((i + 1) * n) >> shift);
+      std::string path = std::string(dir) + "/";
+      if (family == 0) path += std::string(aname) + "." + bname + ".M" + std::to_string(i + 1) + ".las";
+      else             path += std::string(bname) + "." + aname + ".R" + std::to_string(i + 1) + ".las";
+      FILE *f = fopen(path.c_str(), "w");
+      if (f == nullptr) return 1;
+      int64_t novl = 0;
+      for (int64_t x = r0; x < r1; x++) novl += nrec[x];
+      int ts = tspace;
+      fwrite(&novl, sizeof(int64_t), 1, f);
+      fwrite(&ts, sizeof(int), 1, f);
+      if (off[r1] > off[r0])
+        fwrite(v.data() + off[r0], 1, (size_t) (off[r1] - off[r0]), f);
+      fclose(f);
+    }
+  return 0;
+}
+
+int damgpu_report_write_profile(const damgpu_report *rr, const damgpu_block *reads, const char *dir,
+                                const char *aname, int tspace)
+{ const ReportOut *r = reinterpret_cast<const ReportOut *>(rr);
+  std::string base = std::string(dir) + "/." + aname + ".prof";
+  FILE *af = fopen((base + ".anno").c_str(), "w"), *df = fopen((base + ".data").c_str(), "w");
+  if (af == nullptr || df == nullptr) return 1;
+  int size = sizeof(int64_t);
+  fwrite(&reads->nreads, sizeof(int), 1, af);
+  fwrite(&size, sizeof(int), 1, af);
+  int64_t cnt = 0;
+  for (int a = 0; a < reads->nreads; a++)
+    { fwrite(&cnt, sizeof(int64_t), 1, af);
+      cnt += (reads->rlen[a] - 1) / tspace + 2;
+    }
+  fwrite(&cnt, sizeof(int64_t), 1, af);
+  if (!r->prof.empty()) fwrite(r->prof.data(), 1, r->prof.size(), df);
+  fclose(af); fclose(df);
+  return 0;
+}
+
 // ---- layer 1 ----------------------------------------------------------------------------
+
+static MapperH *g_mapper = nullptr;                    // static parmr of the reference (map.c:2885)
+static const void *g_mapper_key = nullptr;
 
 void *damgpu_Sort_Kmers(const damgpu_block *block, int *len)
 { need_gpu();
   DeviceBlock *blk = upload(block);
-  damgpu_index *idx = damgpu_index_build(reinterpret_cast<damgpu_dblock *>(blk));
-  free_block(blk);
-  *len = damgpu_index_len(idx);
-  if (*len == 0)
-    { damgpu_index_free(idx);
+  KmerIndex *idx = reinterpret_cast<KmerIndex *>(damgpu_index_build(reinterpret_cast<damgpu_dblock *>(blk)));
+  *len = idx->len;
+  if (idx->len == 0)
+    { free_index(idx);
+      free_block(blk);
       return nullptr;
     }
+  idx->block = blk;                                    // kept resident with the list
   return idx;
+}
+
+void damgpu_Match_Filter(const damgpu_block *ablock, const damgpu_block *bblock, void *atable,
+                         int alen, void *btable, int blen, int comp, int start)
+{ (void) ablock; (void) bblock;
+  KmerIndex *ai = reinterpret_cast<KmerIndex *>(atable), *bi = reinterpret_cast<KmerIndex *>(btable);
+  if (alen == 0 || blen == 0 || ai == nullptr || bi == nullptr)     // map.c:2955-2956
+    { free_index(bi);
+      return;
+    }
+  if (g_mapper == nullptr || g_mapper_key != atable)
+    { if (g_mapper) damgpu_mapper_free(reinterpret_cast<damgpu_mapper *>(g_mapper));
+      g_mapper = reinterpret_cast<MapperH *>(damgpu_mapper_new(reinterpret_cast<damgpu_dblock *>(ai->block),
+                                                               reinterpret_cast<damgpu_index *>(ai)));
+      g_mapper_key = atable;
+    }
+  damgpu_mapper_match(reinterpret_cast<damgpu_mapper *>(g_mapper),
+                      reinterpret_cast<damgpu_dblock *>(bi->block),
+                      reinterpret_cast<damgpu_index *>(bi), comp, start);
+  free_index(bi);                                      // map.c:3181-3182
+}
+
+void damgpu_Reporter(const char *aname, const damgpu_block *ablock, const char *bname,
+                     const damgpu_block *bblock, const damgpu_align_spec *spec, int mflag)
+{ need_gpu();
+  if (g_mapper == nullptr)
+    fatal("Reporter called before Match_Filter");
+  DeviceBlock *ref = upload(bblock);
+  damgpu_report *rep = damgpu_mapper_report(reinterpret_cast<damgpu_mapper *>(g_mapper),
+                                            reinterpret_cast<damgpu_dblock *>(ref), spec, mflag);
+  free_block(ref);
+  if (mflag & 1)
+    if (damgpu_report_write_las(rep, 0, g_par.sort_path.c_str(), aname, bname, g_par.nthreads, g_par.spacing))
+      fatal("Cannot open .las files in %s for writing", g_par.sort_path.c_str());
+  if (mflag & 2)
+    if (damgpu_report_write_las(rep, 1, g_par.sort_path.c_str(), aname, bname, g_par.nthreads, g_par.spacing))
+      fatal("Cannot open .las files in %s for writing", g_par.sort_path.c_str());
+  if (g_par.verbose)
+    { printf("      %lld mapped segments\n", (long long) damgpu_report_records(rep, (mflag & 1) ? 0 : 1));
+      fflush(stdout);
+    }
+  if (g_par.profile)
+    if (damgpu_report_write_profile(rep, ablock, ".", aname, g_par.spacing))
+      fatal("Cannot write the .prof track");
+  damgpu_report_free(rep);
+  damgpu_mapper_free(reinterpret_cast<damgpu_mapper *>(g_mapper));
+  g_mapper = nullptr; g_mapper_key = nullptr;
 }
 
 }  // extern "C"

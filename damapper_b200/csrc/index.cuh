@@ -24,6 +24,7 @@ struct KmerIndex
   int      len = 0;
   float    ms_extract = 0.f, ms_sort = 0.f;
   int      npass = 0;
+  DeviceBlock *block = nullptr;   // block the list was built from, owned when set (layer 1)
 };
 
 DeviceBlock *upload_block(const uint8_t *bases, const int64_t *boff, const int32_t *rlen,

@@ -359,6 +359,7 @@ KmerIndex *sort_kmers(const DeviceBlock *blk, int K, int suppress, cudaStream_t 
 void free_index(KmerIndex *idx)
 { if (idx == nullptr) return;
   dfree(idx->list);
+  free_block(idx->block);
   delete idx;
 }
 

@@ -115,6 +115,51 @@ void           damgpu_seeds_histogram(const damgpu_seeds *s, int64_t *histo /*[1
 void           damgpu_seeds_download(const damgpu_seeds *s, damgpu_seed *out); /* count+1 recs */
 void           damgpu_seeds_free(damgpu_seeds *s);
 
+/* ---- the per-reads-block mapper: state that persists from Match_Filter calls to Reporter
+ *      (static Report_Arg *parmr, reference map.c:1441-1461,2885) ------------------------------ */
+typedef struct damgpu_mapper damgpu_mapper;
+typedef struct damgpu_report damgpu_report;
+
+/* Candidate chain, reference map.c:1386-1397 (read = index of the read in its block) */
+typedef struct { int32_t read, score, length, bread, comp, afirst, alast, bfirst, blast; } damgpu_candidate;
+
+damgpu_mapper *damgpu_mapper_new(const damgpu_dblock *reads, const damgpu_index *reads_idx);
+void           damgpu_mapper_free(damgpu_mapper *m);
+/* Match_Filter for one reference block in one orientation, from resident handles.  `ref` must
+ * already be complemented when comp != 0; start != 0 resets all candidate lists. */
+void           damgpu_mapper_match(damgpu_mapper *m, const damgpu_dblock *ref,
+                                   const damgpu_index *ref_idx, int comp, int start);
+/* chaining alone from a resident seed set (stage-level parity) */
+void           damgpu_mapper_chain(damgpu_mapper *m, const damgpu_seeds *s, int bstart, int comp,
+                                   int start);
+int64_t        damgpu_mapper_last_hits(const damgpu_mapper *m);
+int64_t        damgpu_mapper_num_candidates(const damgpu_mapper *m);
+/* candidates in (read, list order); jcnt[i] pairs per candidate, jumps = (da,db) int32 pairs;
+ * returns the total number of pairs (call with jumps = NULL to size) */
+int64_t        damgpu_mapper_get_candidates(const damgpu_mapper *m, damgpu_candidate *out,
+                                            int32_t *jcnt, int32_t *jumps, int64_t jmax);
+int64_t        damgpu_mapper_get_cover(const damgpu_mapper *m, int16_t *out, int64_t max);
+
+/* Reporter on resident handles: returns the canonical record streams (40-byte records with the
+ * 4 padding bytes zeroed + trace bytes, no file header) of the M and R families and the -p track */
+damgpu_report *damgpu_mapper_report(damgpu_mapper *m, const damgpu_dblock *wholeref,
+                                    const damgpu_align_spec *spec, int mflag);
+void           damgpu_report_free(damgpu_report *r);
+int64_t        damgpu_report_bytes(const damgpu_report *r, int family /*0=M,1=R,2=prof*/);
+int64_t        damgpu_report_records(const damgpu_report *r, int family);
+void           damgpu_report_copy(const damgpu_report *r, int family, uint8_t *out);
+/* nalign, nwaves, ncells (furthest-reaching cell updates, align.c:887-893), H2 events,
+ * overflow-kernel jobs, empty-band events, alignment-kernel ms (when timing is on, as int us) */
+void           damgpu_report_stats(const damgpu_report *r, int64_t out[8]);
+/* write <dir>/<aname>.<bname>.M<i>.las (family 0) or <dir>/<bname>.<aname>.R<i>.las (family 1),
+ * i = 1..nfiles, reads split as (i*nreads)>>log2(nfiles) (map.c:3148,3250-3261); returns 0 */
+int            damgpu_report_write_las(const damgpu_report *r, int family, const char *dir,
+                                       const char *aname, const char *bname, int nfiles,
+                                       int tspace);
+/* write ./.<aname>.prof.anno/.data (map.c:3295-3318) into dir; returns 0 */
+int            damgpu_report_write_profile(const damgpu_report *r, const damgpu_block *reads,
+                                           const char *dir, const char *aname, int tspace);
+
 #ifdef __cplusplus
 }
 #endif
