@@ -57,7 +57,8 @@ SYMBOLS = {
     "damgpu_index_download": (None, [_P, _P]),
     "damgpu_index_free": (None, [_P]),
     "damgpu_index_device_ptr": (_P, [_P]),
-    "damgpu_index_adopt": (_P, [_P, C.c_int]),
+    "damgpu_index_export": (None, [_P, _P]),
+    "damgpu_index_import": (_P, [_P, C.c_int]),
     "damgpu_seeds_build": (_P, [_P, _P, _P, _P]),
     "damgpu_seeds_count": (C.c_int64, [_P]),
     "damgpu_seeds_limit": (C.c_int, [_P]),
@@ -332,7 +333,7 @@ def map_block(reads: HostBlock, ref_blocks, wholeref: HostBlock, kmer=20, suppre
     """The damapper flow for one reads block (damapper.c:825-879) on the GPU: index the reads,
     then for every reference block Match_Filter forward and complemented (the block is
     complemented on the device), then Reporter against the whole reference.
-    `ref_blocks` is a list of forward HostBlocks.  Returns a dict like oracle.map_block."""
+    `ref_blocks` is a list of forward HostBlocks.  Returns a dict of record streams, the -p track and counters."""
     init()
     set_filter_params(kmer, suppress, nthreads)
     set_options(profile=profile, spacing=spacing, best_tie=best_tie, mem_limit=mem_limit)

@@ -78,6 +78,11 @@ int damgpu_init(int device)
       return 1;
     }
   g_sms = prop.multiProcessorCount;
+  { cudaMemPool_t pool;                                   // keep freed blocks in the pool
+    unsigned long long keep = ~0ull;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
   g_ready = true;
   return 0;
 }
@@ -148,10 +153,21 @@ void damgpu_index_free(damgpu_index *idx) { free_index(reinterpret_cast<KmerInde
 void *damgpu_index_device_ptr(const damgpu_index *idx)
 { return reinterpret_cast<const KmerIndex *>(idx)->list; }
 
-damgpu_index *damgpu_index_adopt(void *device_list, int len)
-{ KmerIndex *idx = new KmerIndex();
-  idx->list = (KmerPos *) device_list;
-  idx->len = len;
+void damgpu_index_export(const damgpu_index *i, void *dst)
+{ const KmerIndex *idx = reinterpret_cast<const KmerIndex *>(i);
+  if (idx->len > 0)
+    CUDA_CHECK(cudaMemcpy(dst, idx->list, sizeof(KmerPos) * ((size_t) idx->len + 2),
+                          cudaMemcpyDeviceToDevice));
+}
+
+damgpu_index *damgpu_index_import(const void *src, int len)
+{ need_gpu();
+  KmerIndex *idx = new KmerIndex();
+  if (len > 0)
+    { idx->list = dalloc<KmerPos>((size_t) len + 2);
+      CUDA_CHECK(cudaMemcpy(idx->list, src, sizeof(KmerPos) * ((size_t) len + 2), cudaMemcpyDeviceToDevice));
+      idx->len = len;
+    }
   return reinterpret_cast<damgpu_index *>(idx);
 }
 

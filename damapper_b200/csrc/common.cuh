@@ -33,14 +33,18 @@ extern unsigned long long g_launches;
        KERNEL_CHECK();                                                \
   } while (0)
 
+// Device memory comes from the stream-ordered pool of the default stream (cudaMallocAsync) with
+// an unlimited release threshold: after the first step every buffer is recycled inside the
+// process instead of being mapped/unmapped by the driver (GB-sized cudaMalloc/cudaFree calls
+// cost more host time than the kernels that use them).
 template <typename T> static inline T *dalloc(size_t n)
 { T *p = nullptr;
   if (n == 0) n = 1;
-  CUDA_CHECK(cudaMalloc((void **) &p, n * sizeof(T)));
+  CUDA_CHECK(cudaMallocAsync((void **) &p, n * sizeof(T), 0));
   return p;
 }
 
-static inline void dfree(void *p) { if (p) CUDA_CHECK(cudaFree(p)); }
+static inline void dfree(void *p) { if (p) CUDA_CHECK(cudaFreeAsync(p, 0)); }
 
 int sm_count();
 

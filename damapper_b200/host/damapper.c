@@ -1,0 +1,356 @@
+/* damapper host driver for libdamgpu: keeps the reference command line
+ *   damapper [-vpzCN] [-k<int(20)>] [-t<int>] [-M<int>] [-T<int(4)>] [-P<dir(/tmp)>]
+ *            [-e<double(.85)] [-s<int(100)>] [-n<double(1.00)>] [-m<track>]+ <reference:dam> <reads:db> ...
+ * (reference damapper.c:52-56,556-922), DAZZ_DB .db/.dam input and the per-thread .las output,
+ * and calls the CUDA mapping core through the C ABI of include/libdamgpu.h.  Everything that
+ * used to sit behind map.h runs on the GPU; this file only parses flags, loads blocks, and
+ * runs the same LAsort/LAcat/LAmerge post-processing commands as the reference.
+ *
+ * The reference block is uploaded once per block, indexed, matched, reverse-complemented ON
+ * THE DEVICE and indexed/matched again (the reference complements on the host and re-sorts,
+ * damapper.c:847-861).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+#include <dirent.h>
+#include <sys/stat.h>
+#include <sys/types.h>
+#include "dazz_db.h"
+
+static const char *Prog_Name = "damapper";
+static char *SORT_PATH = "/tmp";
+
+static const char *Usage[] =
+  { "[-vpzCN] [-k<int(20)>] [-t<int>] [-M<int>] [-T<int(4)>] [-P<dir(/tmp)>]",
+    "         [-e<double(.85)] [-s<int(100)>] [-n<double(1.00)>]",
+    "         [-m<track>]+  <reference:dam> <reads:db> ...",
+  };
+
+static void Clean_Exit(int val)                       /* damapper.c:543-554 */
+{ char command[8192];
+  snprintf(command,sizeof(command),"rm -r %s",SORT_PATH);
+  if (system(command) != 0)
+    { fprintf(stderr,"%s: Command Failed:\n%*s      %s\n",Prog_Name,(int) strlen(Prog_Name),"",command);
+      exit (1);
+    }
+  exit (val);
+}
+
+static uint64_t physical_memory(void)                  /* damapper.c:74-141, Linux branch */
+{ long pages = sysconf(_SC_PHYS_PAGES), psize = sysconf(_SC_PAGESIZE);
+  if (pages <= 0 || psize <= 0)
+    return (0);
+  return ((uint64_t) pages * (uint64_t) psize);
+}
+
+static int arg_int(const char *arg, const char *what, int positive)
+{ char *e;
+  long v = strtol(arg+2,&e,10);
+  if (*e != '\0' || arg[2] == '\0')
+    { fprintf(stderr,"%s: -%c '%s' argument is not an integer\n",Prog_Name,arg[1],arg+2);
+      exit (1);
+    }
+  if (positive ? v <= 0 : v < 0)
+    { fprintf(stderr,"%s: %s must be %s (%ld)\n",Prog_Name,what,positive ? "positive" : "non-negative",v);
+      exit (1);
+    }
+  return ((int) v);
+}
+
+static double arg_real(const char *arg)
+{ char *e;
+  double v = strtod(arg+2,&e);
+  if (*e != '\0' || arg[2] == '\0')
+    { fprintf(stderr,"%s: -%c '%s' argument is not a real number\n",Prog_Name,arg[1],arg+2);
+      exit (1);
+    }
+  return (v);
+}
+
+#define SYSTEM_CHECK(command)                                           \
+ { if (VERBOSE)                                                         \
+     printf("%s\n",command);                                            \
+   if (system(command) != 0)                                            \
+     { fprintf(stderr,"\n%s: Command Failed:\n%*s      %s\n",           \
+                      Prog_Name,(int) strlen(Prog_Name),"",command);    \
+       Clean_Exit(1);                                                   \
+     }                                                                  \
+ }
+
+int main(int argc, char *argv[])
+{ int    VERBOSE = 0, PROFILE = 0, COVER = 0, NOMAP = 0, MAP_ORDER = 1;
+  int    KMER_LEN = 20, MAX_REPS = 0, NTHREADS = 4, SPACING = 100, MTOP = 0;
+  double AVE_ERROR = .85, BEST_TIE = 1.0;
+  uint64_t MEM_PHYSICAL, MEM_LIMIT;
+  int    mflag, i, j, k;
+  DIR   *dirp;
+  Dazz_Block refdb, ablock, bblock;
+  damgpu_options opts;
+  damgpu_align_spec spec;
+
+  MEM_PHYSICAL = physical_memory();
+  MEM_LIMIT    = MEM_PHYSICAL;
+  if (MEM_PHYSICAL == 0)
+    { fprintf(stderr,"\nWarning: Could not get physical memory size\n");
+      fflush(stderr);
+    }
+
+  j = 1;
+  for (i = 1; i < argc; i++)
+    if (argv[i][0] == '-')
+      switch (argv[i][1])
+      { default:
+          for (k = 1; argv[i][k] != '\0'; k++)
+            switch (argv[i][k])
+            { case 'v': VERBOSE = 1; break;
+              case 'p': PROFILE = 1; break;
+              case 'z': MAP_ORDER = 0; break;
+              case 'C': COVER = 1; break;
+              case 'N': NOMAP = 1; break;
+              default:
+                fprintf(stderr,"%s: -%c is an illegal option\n",Prog_Name,argv[i][k]);
+                exit (1);
+            }
+          break;
+        case 'e':
+          AVE_ERROR = arg_real(argv[i]);
+          if (AVE_ERROR < .7 || AVE_ERROR >= 1.)
+            { fprintf(stderr,"%s: Average correlation must be in [.7,1.) (%g)\n",Prog_Name,AVE_ERROR);
+              exit (1);
+            }
+          break;
+        case 'k':
+          KMER_LEN = arg_int(argv[i],"K-mer length",1);
+          if (KMER_LEN > 32)
+            { fprintf(stderr,"%s: K-mer length must be 32 or less\n",Prog_Name);
+              exit (1);
+            }
+          break;
+        case 'm':
+          MTOP += 1;
+          break;
+        case 'n':
+          BEST_TIE = arg_real(argv[i]);
+          if (BEST_TIE < .7 || BEST_TIE > 1.)
+            { fprintf(stderr,"%s: Near optimal threshold must be in [.7,1.] (%g)\n",Prog_Name,BEST_TIE);
+              exit (1);
+            }
+          break;
+        case 's':
+          SPACING = arg_int(argv[i],"Trace spacing",1);
+          break;
+        case 't':
+          MAX_REPS = arg_int(argv[i],"Tuple supression frequency",1);
+          break;
+        case 'M':
+          MEM_LIMIT = (uint64_t) arg_int(argv[i],"Memory allocation (in Gb)",0) * 0x40000000ull;
+          break;
+        case 'P':
+          SORT_PATH = argv[i]+2;
+          if ((dirp = opendir(SORT_PATH)) == NULL)
+            { fprintf(stderr,"%s: -P option: cannot open directory %s\n",Prog_Name,SORT_PATH);
+              exit (1);
+            }
+          closedir(dirp);
+          break;
+        case 'T':
+          NTHREADS = arg_int(argv[i],"Number of threads",1);
+          break;
+      }
+    else
+      argv[j++] = argv[i];
+  argc = j;
+
+  if (argc <= 2)
+    { fprintf(stderr,"Usage: %s %s\n",Prog_Name,Usage[0]);
+      fprintf(stderr,"       %*s %s\n",(int) strlen(Prog_Name),"",Usage[1]);
+      fprintf(stderr,"       %*s %s\n",(int) strlen(Prog_Name),"",Usage[2]);
+      fprintf(stderr,"\n");
+      fprintf(stderr,"      -k: k-mer size (must be <= 32).\n");
+      fprintf(stderr,"      -t: Ignore k-mers that occur >= -t times in a block.\n");
+      fprintf(stderr,"      -M: Use only -M GB of memory by ignoring most frequent k-mers.\n");
+      fprintf(stderr,"\n");
+      fprintf(stderr,"      -e: Look for alignments with -e percent similarity.\n");
+      fprintf(stderr,"      -s: Use -s as the trace point spacing for encoding alignments.\n");
+      fprintf(stderr,"      -n: Output all matches within this %% of the best\n");
+      fprintf(stderr,"\n");
+      fprintf(stderr,"      -T: Use -T threads (here: number of per-range .las files).\n");
+      fprintf(stderr,"      -P: Do sorts and merges in directory -P.\n");
+      fprintf(stderr,"      -m: Soft mask the blocks with the specified mask.\n");
+      fprintf(stderr,"\n");
+      fprintf(stderr,"      -v: Verbose mode, output statistics as proceed.\n");
+      fprintf(stderr,"      -z: sort .las by A,B-read pairs (overlap piles)\n");
+      fprintf(stderr,"          off => sort .las by A-read,A-position pairs (default for mapping)\n");
+      fprintf(stderr,"      -p: Output repeat profile track\n");
+      fprintf(stderr,"      -C: Output reference vs reads .las.\n");
+      fprintf(stderr,"      -N: Do not output reads vs reference .las.\n");
+      exit (1);
+    }
+
+  if (COVER)
+    mflag = NOMAP ? 2 : 3;                              /* FLAG_DOB / FLAG_DOA|FLAG_DOB */
+  else if (NOMAP)
+    { fprintf(stderr,"%s: Cannot specify N flag without C also\n",Prog_Name);
+      exit (1);
+    }
+  else
+    mflag = 1;
+  if (NOMAP && PROFILE)
+    { fprintf(stderr,"%s: Cannot specify both N and p flags together\n",Prog_Name);
+      exit (1);
+    }
+  if (MTOP > 0)
+    { fprintf(stderr,"%s: -m mask tracks are not supported by the GPU core yet; refusing to"
+                     " ignore the mask\n",Prog_Name);
+      exit (1);
+    }
+
+  /* reference: stub, block count, base frequencies (damapper.c:734-797) */
+  if (dazz_open(argv[1],&refdb) != 0)
+    exit (1);
+  if (refdb.part > 0)
+    { fprintf(stderr,"%s: first argument '%s' cannot be a block\n",Prog_Name,argv[1]);
+      exit (1);
+    }
+  if (refdb.nblocks == 0)
+    { fprintf(stderr,"%s: DB %s has not yet been partitioned, cannot request a block !\n",
+                     Prog_Name,refdb.root);
+      exit (1);
+    }
+  spec.ave_corr = AVE_ERROR;
+  spec.trace_space = SPACING;
+  memcpy(spec.freq,refdb.freq,sizeof(spec.freq));
+
+  { const char *dev = getenv("DAMGPU_DEVICE");
+    if (damgpu_init(dev ? atoi(dev) : -1) != 0)
+      { fprintf(stderr,"%s: no usable CUDA device (%s); this build has no CPU path\n",
+                       Prog_Name,damgpu_last_error());
+        exit (1);
+      }
+  }
+  if (damgpu_Set_Filter_Params(KMER_LEN,MAX_REPS,NTHREADS))
+    { fprintf(stderr,"Illegal combination of filter parameters\n");
+      exit (1);
+    }
+
+  { char *newpath = (char *) malloc(strlen(SORT_PATH)+30);   /* damapper.c:806-817 */
+    sprintf(newpath,"%s/damapper.%d",SORT_PATH,getpid());
+    if (mkdir(newpath,S_IRWXU) != 0)
+      { fprintf(stderr,"%s: Could not create directory %s\n",Prog_Name,newpath);
+        exit (1);
+      }
+    SORT_PATH = newpath;
+  }
+  opts.verbose = VERBOSE; opts.profile = PROFILE; opts.spacing = SPACING; opts.best_tie = BEST_TIE;
+  opts.sort_path = SORT_PATH; opts.mem_limit = MEM_LIMIT; opts.mem_physical = MEM_PHYSICAL;
+  damgpu_set_options(&opts);
+  damgpu_set_fatal(Clean_Exit);
+
+  for (i = 2; i < argc; i++)                              /* damapper.c:825-914 */
+    { char *broot, *aroot = refdb.root, name[4096], command[16384];
+      damgpu_block  bview, aview;
+      damgpu_dblock *dreads, *dref;
+      damgpu_index  *bindex, *aindex;
+      damgpu_mapper *mapper;
+      damgpu_report *rep;
+
+      if (dazz_load(argv[i],&bblock) != 0)
+        Clean_Exit(1);
+      for (k = 0; k < bblock.nreads; k++)
+        if (bblock.rlen[k] < KMER_LEN)
+          { fprintf(stderr,"%s: Block %s contains reads < %dbp long !  Run DBsplit -x%d\n",
+                           Prog_Name,argv[i],KMER_LEN,KMER_LEN);
+            Clean_Exit(1);
+          }
+      if (bblock.part > 0)
+        { broot = (char *) malloc(strlen(bblock.root)+20);
+          sprintf(broot,"%s.%d",bblock.root,bblock.part);
+        }
+      else
+        broot = strdup(bblock.root);
+      dazz_view(&bblock,&bview);
+      if (VERBOSE)
+        printf("\nBuilding index for %s\n",broot);
+      dreads = damgpu_block_upload(&bview);
+      bindex = damgpu_index_build(dreads);
+      mapper = damgpu_mapper_new(dreads,bindex);
+
+      for (k = 1; k <= refdb.nblocks; k++)
+        { snprintf(name,sizeof(name),"%s/%s.%d.%s",refdb.pwd,aroot,k,refdb.isdam ? "dam" : "db");
+          if (dazz_load(name,&ablock) != 0)
+            Clean_Exit(1);
+          dazz_view(&ablock,&aview);
+          if (VERBOSE)
+            printf("\nBuilding index for %s.%d\n",aroot,k);
+          dref = damgpu_block_upload(&aview);
+          aindex = damgpu_index_build(dref);
+          if (VERBOSE)
+            printf("\nComparing %s to %s.%d\n",broot,aroot,k);
+          damgpu_mapper_match(mapper,dref,aindex,0,(k == 1));
+          damgpu_index_free(aindex);
+
+          damgpu_block_complement(dref);
+          if (VERBOSE)
+            printf("\nBuilding index for c(%s.%d)\n",aroot,k);
+          aindex = damgpu_index_build(dref);
+          if (VERBOSE)
+            printf("\nComparing %s to c(%s.%d)\n",broot,aroot,k);
+          damgpu_mapper_match(mapper,dref,aindex,1,0);
+          damgpu_index_free(aindex);
+          damgpu_block_free(dref);
+          dazz_close(&ablock);
+        }
+
+      snprintf(name,sizeof(name),"%s/%s.%s",refdb.pwd,aroot,refdb.isdam ? "dam" : "db");
+      if (dazz_load(name,&ablock) != 0)
+        Clean_Exit(1);
+      dazz_view(&ablock,&aview);
+      if (VERBOSE)
+        printf("\nFinding best matches for block %s\n",broot);
+      dref = damgpu_block_upload(&aview);
+      rep  = damgpu_mapper_report(mapper,dref,&spec,mflag);
+      { int nfiles = 1;
+        while (2*nfiles <= NTHREADS) nfiles *= 2;
+        if ((mflag & 1) && damgpu_report_write_las(rep,0,SORT_PATH,broot,aroot,nfiles,SPACING))
+          Clean_Exit(1);
+        if ((mflag & 2) && damgpu_report_write_las(rep,1,SORT_PATH,broot,aroot,nfiles,SPACING))
+          Clean_Exit(1);
+        if (PROFILE && damgpu_report_write_profile(rep,&bview,".",broot,SPACING))
+          Clean_Exit(1);
+      }
+      if (VERBOSE)
+        { printf("      %lld mapped segments\n",(long long) damgpu_report_records(rep,(mflag & 1) ? 0 : 1));
+          fflush(stdout);
+        }
+      damgpu_report_free(rep);
+      damgpu_block_free(dref);
+      dazz_close(&ablock);
+      damgpu_mapper_free(mapper);
+      damgpu_index_free(bindex);
+      damgpu_block_free(dreads);
+      dazz_close(&bblock);
+
+      if ((mflag & 1) != 0)                              /* damapper.c:893-901 */
+        { sprintf(command,"LAsort %s %s %s/%s.%s.M%c.las",VERBOSE?"-v":"",MAP_ORDER?"-a":"",
+                          SORT_PATH,broot,aroot,'@');
+          SYSTEM_CHECK(command)
+          sprintf(command,"LAcat %s %s/%s.%s.M%c.S >%s.%s.las",VERBOSE?"-v":"",
+                          SORT_PATH,broot,aroot,'@',broot,aroot);
+          SYSTEM_CHECK(command)
+        }
+      if ((mflag & 2) != 0)                              /* damapper.c:903-911 */
+        { sprintf(command,"LAsort %s %s %s/%s.%s.R%c.las",VERBOSE?"-v":"",MAP_ORDER?"-a":"",
+                          SORT_PATH,aroot,broot,'@');
+          SYSTEM_CHECK(command)
+          sprintf(command,"LAmerge %s %s %s.%s %s/%s.%s.R%c.S.las",VERBOSE?"-v":"",MAP_ORDER?"-a":"",
+                          aroot,broot,SORT_PATH,aroot,broot,'@');
+          SYSTEM_CHECK(command)
+        }
+      free(broot);
+    }
+
+  Clean_Exit(0);
+  return (0);
+}

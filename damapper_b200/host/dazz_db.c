@@ -1,0 +1,262 @@
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "dazz_db.h"
+
+#define DB_BEST 0x800      /* DB.h:278 */
+#define DB_ALL  0x1
+
+/* raw .idx records, LP64 layout (DB.h:285-295,390-420) */
+typedef struct
+  { int32_t ureads, treads, cutoff, allarr;
+    float   freq[4];
+    int32_t maxlen, pad0;
+    int64_t totlen;
+    int32_t nreads, trimmed, part, ufirst, tfirst, pad1;
+    int64_t path;
+    int32_t loaded, pad2;
+    int64_t bases, reads, tracks;
+  } Idx_Header;
+
+typedef struct
+  { int32_t origin, rlen, fpulse, pad0;
+    int64_t boff, coff;
+    int32_t flags, pad1;
+  } Idx_Read;
+
+static char *dup_range(const char *s, size_t n)
+{ char *r = (char *) malloc(n+1);
+  memcpy(r,s,n);
+  r[n] = '\0';
+  return (r);
+}
+
+/* split "dir/root[.N][.db|.dam]" */
+static void split_name(const char *name, char **pwd, char **root, int *part, int *ext)
+{ const char *slash = strrchr(name,'/');
+  const char *base = slash ? slash+1 : name;
+  size_t len = strlen(base);
+  *ext = 0;
+  if (len > 4 && strcmp(base+len-4,".dam") == 0) { len -= 4; *ext = 2; }
+  else if (len > 3 && strcmp(base+len-3,".db") == 0) { len -= 3; *ext = 1; }
+  *pwd = slash ? dup_range(name,(size_t) (slash-name)) : dup_range(".",1);
+  *part = 0;
+  { size_t i = len;
+    while (i > 0 && base[i-1] >= '0' && base[i-1] <= '9') i--;
+    if (i < len && i > 1 && base[i-1] == '.')
+      { *part = atoi(base+i);
+        if (*part > 0) len = i-1; else *part = 0;
+      }
+  }
+  *root = dup_range(base,len);
+}
+
+static FILE *open_stub(Dazz_Block *db, int ext)
+{ char path[4096];
+  FILE *f = NULL;
+  if (ext != 2)
+    { snprintf(path,sizeof(path),"%s/%s.db",db->pwd,db->root);
+      if ((f = fopen(path,"r")) != NULL) { db->isdam = 0; return (f); }
+    }
+  snprintf(path,sizeof(path),"%s/%s.dam",db->pwd,db->root);
+  if ((f = fopen(path,"r")) != NULL) { db->isdam = 1; return (f); }
+  return (NULL);
+}
+
+int dazz_open(const char *name, Dazz_Block *db)
+{ int  ext, nfiles, i, x;
+  char a[2048], b[2048];
+  FILE *f;
+
+  memset(db,0,sizeof(*db));
+  split_name(name,&db->pwd,&db->root,&db->part,&ext);
+  if ((f = open_stub(db,ext)) == NULL)
+    { fprintf(stderr,"damapper: Could not open database %s\n",name);
+      return (-1);
+    }
+  if (fscanf(f,"files = %9d\n",&nfiles) != 1)
+    { fprintf(stderr,"damapper: Stub file (.db) of %s is junk\n",db->root);
+      fclose(f);
+      return (-1);
+    }
+  for (i = 0; i < nfiles; i++)
+    if (fscanf(f,"  %9d %2047s %2047s\n",&x,a,b) != 3)
+      { fprintf(stderr,"damapper: Stub file (.db) of %s is junk\n",db->root);
+        fclose(f);
+        return (-1);
+      }
+  if (fscanf(f,"blocks = %9d\n",&db->nblocks) != 1)
+    db->nblocks = 0;
+  fclose(f);
+
+  { char path[4096];
+    Idx_Header h;
+    snprintf(path,sizeof(path),"%s/.%s.idx",db->pwd,db->root);
+    if ((f = fopen(path,"r")) == NULL || fread(&h,sizeof(h),1,f) != 1)
+      { fprintf(stderr,"damapper: Index file (.idx) of %s is junk\n",db->root);
+        if (f) fclose(f);
+        return (-1);
+      }
+    fclose(f);
+    memcpy(db->freq,h.freq,sizeof(db->freq));
+  }
+  db->path_len = (int64_t) (strlen(db->pwd) + 2 + strlen(db->root));
+  return (0);
+}
+
+int dazz_load(const char *name, Dazz_Block *db)
+{ char  path[4096], a[2048], b[2048];
+  FILE *f;
+  int   ext, nfiles, nblocks = 0, cutoff = 0, all = 1, i, x;
+  long long size;
+  int   ufirst = 0, ulast, tfirst = 0;
+  Idx_Header h;
+  Idx_Read  *recs;
+
+  if (dazz_open(name,db) != 0)
+    return (-1);
+  split_name(name,&db->pwd,&db->root,&db->part,&ext);
+
+  if ((f = open_stub(db,ext)) == NULL)
+    return (-1);
+  if (fscanf(f,"files = %9d\n",&nfiles) != 1) { fclose(f); return (-1); }
+  for (i = 0; i < nfiles; i++)
+    if (fscanf(f,"  %9d %2047s %2047s\n",&x,a,b) != 3) { fclose(f); return (-1); }
+  if (fscanf(f,"blocks = %9d\n",&nblocks) == 1)
+    { if (fscanf(f,"size = %11lld cutoff = %9d all = %1d\n",&size,&cutoff,&all) != 3)
+        { fprintf(stderr,"damapper: Stub file (.db) of %s is junk\n",db->root);
+          fclose(f);
+          return (-1);
+        }
+    }
+  else if (db->part > 0)
+    { fprintf(stderr,"damapper: DB %s has not yet been partitioned, cannot request a block !\n",db->root);
+      fclose(f);
+      return (-1);
+    }
+
+  snprintf(path,sizeof(path),"%s/.%s.idx",db->pwd,db->root);
+  { FILE *g = fopen(path,"r");
+    if (g == NULL || fread(&h,sizeof(h),1,g) != 1)
+      { fprintf(stderr,"damapper: Index file (.idx) of %s is junk\n",db->root);
+        fclose(f);
+        return (-1);
+      }
+    recs = (Idx_Read *) malloc(sizeof(Idx_Read)*(size_t) (h.ureads+1));
+    if (fread(recs,sizeof(Idx_Read),(size_t) h.ureads,g) != (size_t) h.ureads)
+      { fprintf(stderr,"damapper: Index file (.idx) of %s is junk\n",db->root);
+        fclose(g); fclose(f);
+        return (-1);
+      }
+    fclose(g);
+  }
+  if (nblocks == 0)
+    { cutoff = h.cutoff < 0 ? 0 : h.cutoff;
+      all = (h.allarr & DB_ALL) != 0;
+    }
+  ulast = h.ureads;
+  if (db->part > 0)
+    { int uf = 0, tf = 0, ul = 0, tl = 0;
+      if (db->part > nblocks)
+        { fprintf(stderr,"damapper: DB %s has only %d blocks\n",db->root,nblocks);
+          fclose(f);
+          return (-1);
+        }
+      for (i = 0; i <= db->part; i++)
+        { uf = ul; tf = tl;
+          if (fscanf(f," %9d %9d\n",&ul,&tl) != 2)
+            { fprintf(stderr,"damapper: Stub file (.db) of %s is junk\n",db->root);
+              fclose(f);
+              return (-1);
+            }
+        }
+      ufirst = uf; ulast = ul; tfirst = tf;
+    }
+  fclose(f);
+  db->cutoff = cutoff; db->all = all; db->nblocks = nblocks;
+
+  /* trim (Trim_DB semantics: keep reads >= cutoff that are the best of their well unless all) */
+  { int     n = 0, u;
+    int64_t tot = 0, o = 0;
+    int     maxlen = 0;
+    FILE   *bps;
+
+    for (u = ufirst; u < ulast; u++)
+      if ((all || (recs[u].flags & DB_BEST)) && recs[u].rlen >= cutoff)
+        { n += 1; tot += recs[u].rlen;
+          if (recs[u].rlen > maxlen) maxlen = recs[u].rlen;
+        }
+    db->nreads = n; db->tfirst = tfirst; db->totlen = tot; db->maxlen = maxlen;
+    db->raw  = (uint8_t *) malloc((size_t) (tot + n + 8));
+    db->boff = (int64_t *) malloc(sizeof(int64_t)*(size_t) (n+1));
+    db->rlen = (int32_t *) malloc(sizeof(int32_t)*(size_t) (n+1));
+    if (db->raw == NULL || db->boff == NULL || db->rlen == NULL)
+      { fprintf(stderr,"damapper: Out of memory (Allocating All Sequence Reads)\n");
+        return (-1);
+      }
+    snprintf(path,sizeof(path),"%s/.%s.bps",db->pwd,db->root);
+    if ((bps = fopen(path,"r")) == NULL)
+      { fprintf(stderr,"damapper: Cannot open %s\n",path);
+        return (-1);
+      }
+    db->raw[0] = 4;
+    n = 0;
+    for (u = ufirst; u < ulast; u++)
+      if ((all || (recs[u].flags & DB_BEST)) && recs[u].rlen >= cutoff)
+        { int      len = recs[u].rlen, clen = (len+3) >> 2, j;
+          uint8_t *s = db->raw + 1 + o;
+          uint8_t *c = s + (len - clen);           /* read the packed bytes into the tail */
+          if (len < 0 || fseeko(bps,recs[u].boff,SEEK_SET) != 0 ||
+              (clen > 0 && fread(c,1,(size_t) clen,bps) != (size_t) clen))
+            { fprintf(stderr,"damapper: Read of .bps file failed\n");
+              fclose(bps);
+              return (-1);
+            }
+          for (j = 0; j < len; j++)                /* first base in the two top bits */
+            s[j] = (uint8_t) ((c[j >> 2] >> (6 - 2*(j & 3))) & 3);
+          s[len] = 4;
+          db->boff[n] = o;
+          db->rlen[n] = len;
+          o += len+1;
+          n += 1;
+        }
+    db->boff[n] = o;
+    fclose(bps);
+  }
+  free(recs);
+  return (0);
+}
+
+void dazz_close(Dazz_Block *db)
+{ free(db->raw); free(db->boff); free(db->rlen); free(db->root); free(db->pwd);
+  memset(db,0,sizeof(*db));
+}
+
+void dazz_complement(Dazz_Block *db)
+{ int i;
+  float x;
+  x = db->freq[0]; db->freq[0] = db->freq[3]; db->freq[3] = x;
+  x = db->freq[1]; db->freq[1] = db->freq[2]; db->freq[2] = x;
+  for (i = 0; i < db->nreads; i++)
+    { uint8_t *s = db->raw + 1 + db->boff[i], *t = s + db->rlen[i] - 1;
+      while (s < t)
+        { uint8_t c = *s;
+          *s++ = (uint8_t) (3 - *t);
+          *t-- = (uint8_t) (3 - c);
+        }
+      if (s == t)
+        *s = (uint8_t) (3 - *s);
+    }
+}
+
+void dazz_view(const Dazz_Block *db, damgpu_block *v)
+{ v->bases = db->raw + 1;
+  v->boff = db->boff;
+  v->rlen = db->rlen;
+  v->nreads = db->nreads;
+  v->tfirst = db->tfirst;
+  v->maxlen = db->maxlen;
+  v->totlen = db->totlen;
+  /* sizeof_DB, DB.c:1044-1051: sizeof(DAZZ_DB)=112, sizeof(DAZZ_READ)=40 */
+  v->sizeof_db = 112 + 40*((int64_t) db->nreads+2) + db->path_len + 1 + (db->totlen + db->nreads + 4);
+}

@@ -1,0 +1,37 @@
+/* Minimal reader of DAZZ_DB databases (.db / .dam stub, .<root>.idx, .<root>.bps) for the
+ * damgpu host driver.  Written from the on-disk layout (reference DB.h:285-295,390-435 and
+ * DB.c:319-363): it loads one block, trimmed, as one byte per base with 4-terminators -- the
+ * image Load_All_Reads builds (DB.c:1389-1441) -- ready to hand to libdamgpu. */
+#ifndef DAMGPU_DAZZ_DB_H
+#define DAMGPU_DAZZ_DB_H
+
+#include <stdint.h>
+#include "../../include/libdamgpu.h"
+
+typedef struct
+  { char    *root;        /* root name without extension / block suffix */
+    char    *pwd;         /* directory */
+    int      isdam;
+    int      nblocks;     /* 0 if the DB has not been split */
+    int      part;        /* block that was loaded, 0 = whole DB */
+    float    freq[4];
+    int      cutoff, all;
+    /* loaded (trimmed) block */
+    int      nreads, tfirst, maxlen;
+    int64_t  totlen;
+    uint8_t *raw;         /* allocation; bases = raw+1, raw[0] = 4 */
+    int64_t *boff;        /* nreads+1 */
+    int32_t *rlen;
+    int64_t  path_len;    /* strlen(db->path) of the reference, enters sizeof_DB (DB.c:1050) */
+  } Dazz_Block;
+
+/* Reads the stub: fills root/pwd/isdam/nblocks/freq.  Returns 0, or -1 after printing why. */
+int  dazz_open(const char *name, Dazz_Block *db);
+/* Loads block `part` (0 = all, or the .N suffix given in `name`) with all reads in memory. */
+int  dazz_load(const char *name, Dazz_Block *db);
+void dazz_close(Dazz_Block *db);
+/* In-place reverse complement of every read (complement_DB, damapper.c:433-469). */
+void dazz_complement(Dazz_Block *db);
+void dazz_view(const Dazz_Block *db, damgpu_block *view);
+
+#endif

@@ -104,7 +104,10 @@ void           damgpu_index_download(const damgpu_index *idx, damgpu_kmer *out);
 void           damgpu_index_free(damgpu_index *idx);
 /* raw device pointer of the list (len+2 records), for NCCL broadcast by the caller */
 void          *damgpu_index_device_ptr(const damgpu_index *idx);
-damgpu_index  *damgpu_index_adopt(void *device_list, int len);             /* takes ownership */
+/* device-to-device copies out of / into a caller-owned device buffer of (len+2)*16 bytes, so a
+ * collective library (NCCL through torch.distributed) can move an index between GPUs */
+void           damgpu_index_export(const damgpu_index *idx, void *device_dst);
+damgpu_index  *damgpu_index_import(const void *device_src, int len);
 
 /* merge-join + seed sort of Match_Filter (map.c:2958-3126) as a separate stage */
 damgpu_seeds  *damgpu_seeds_build(const damgpu_index *reads_idx, const damgpu_dblock *reads,

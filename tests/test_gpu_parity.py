@@ -1,0 +1,274 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI
+(damapper_b200.api -> libdamgpu.so), against the oracle on the same seeded inputs, against the
+committed golden vectors of the reference, and through size-independent properties at the
+benchmark's full size.  All work is integer: every comparison is bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, base_freq, make_case
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def api():
+    from damapper_b200 import api as a
+    a.init()          # raises without a B200: there is no fallback
+    return a
+
+
+def _gpu_vs_oracle(api, orc, cfg, scale, seed, **kw):
+    contigs, rb, rl, rd, rf, rc = make_case(cfg, scale, seed)
+    freq = base_freq(contigs)
+    o = orc.map_block(orc.HostBlock(*rd), [(orc.HostBlock(*rf), orc.HostBlock(*rc))],
+                      orc.HostBlock(*rf), freq=freq, **kw)
+    g = api.map_block(api.HostBlock(*rd), [api.HostBlock(*rf)], api.HostBlock(*rf), freq=freq,
+                      want_candidates=True, **kw)
+    oc, ojc, oj = o["candidates"]
+    gc, gjc, gj = g["candidates"]
+    assert oc.tobytes() == gc.tobytes(), "candidate chains differ"
+    assert (ojc == gjc).all() and oj.tobytes() == gj.tobytes(), "Jump lists differ"
+    assert g["a"] == o["a"], "M records differ"
+    assert g["b"] == o["b"], "R records differ"
+    assert g["prof"] == o["prof"], "-p track differs"
+    for key in ("nalign", "nwaves", "ncells"):
+        assert g["stats"][key] == o["stats"][key], key
+    return g
+
+
+@pytest.mark.parametrize("case", ["c1_default", "c5_cover_profile", "c3_repeat_n95",
+                                  "c1_k16_s50_t20_e80", "c1_k24_s200"])
+def test_gpu_matches_reference_golden(api, case):
+    """CUDA output == the unmodified reference's output (committed fixtures)."""
+    from oracle.make_golden import CASES, input_digest
+    cfg, scale, seed, flags, kw = CASES[case]
+    contigs, rb, rl, rd, rf, rc = make_case(cfg, scale, seed)
+    g = np.load(os.path.join(GOLDEN, case + ".npz"))
+    assert input_digest(contigs, rb, rl) == str(g["digest"])
+    out = api.map_block(api.HostBlock(*rd), [api.HostBlock(*rf)], api.HostBlock(*rf),
+                        freq=base_freq(contigs), **kw)
+    assert out["a"] == g["a"].tobytes()
+    assert out["b"] == g["b"].tobytes()
+    assert out["prof"] == g["prof"].tobytes()
+
+
+@pytest.mark.parametrize("cfg,scale,seed,kw", [
+    ("C1", 0.1, 4, dict(do_b=1)),
+    ("C1", 0.25, 31, dict()),
+    ("C5", 0.2, 14, dict(do_b=1, best_tie=0.8)),
+    ("C5", 0.3, 32, dict(do_b=1, profile=1)),
+    ("C3", 0.004, 16, dict(do_b=1, profile=1, best_tie=0.7)),
+    ("C3", 0.01, 33, dict(profile=1, best_tie=0.95)),
+    ("C2", 0.02, 34, dict()),
+    ("C1", 0.05, 18, dict(kmer=14, ave_corr=0.8, suppress=20, do_b=1)),
+    ("C1", 0.05, 35, dict(kmer=32, spacing=75)),
+    ("C1", 0.05, 36, dict(kmer=12, ave_corr=0.7, spacing=126, do_b=1)),
+])
+def test_pipeline_matches_oracle(api, oracle_mod, cfg, scale, seed, kw):
+    _gpu_vs_oracle(api, oracle_mod, cfg, scale, seed, **kw)
+
+
+@pytest.mark.parametrize("cfg,scale,seed,kmer,suppress", [
+    ("C1", 0.1, 4, 20, 0), ("C3", 0.002, 5, 14, 0), ("C1", 0.05, 6, 16, 10),
+    ("C5", 0.1, 7, 32, 0), ("C1", 0.05, 8, 12, 0), ("C1", 0.05, 9, 9, 3),
+])
+def test_index_and_seeds_match_oracle(api, oracle_mod, cfg, scale, seed, kmer, suppress):
+    """Sort_Kmers (a2-a5) and merge-join + seed sort (a6-a9) arrays, byte for byte."""
+    orc = oracle_mod
+    contigs, rb, rl, rd, rf, rc = make_case(cfg, scale, seed)
+    api.set_filter_params(kmer, suppress, 4)
+    api.set_options()
+    hr, hg = api.HostBlock(*rd), api.HostBlock(*rf)
+    dr, dg = api.DeviceBlock(hr), api.DeviceBlock(hg)
+    ir, ig = api.Index(dr), api.Index(dg)
+    o_r = orc.sort_kmers(orc.HostBlock(*rd), kmer, suppress)
+    o_g = orc.sort_kmers(orc.HostBlock(*rf), kmer, suppress)
+    assert ir.download().tobytes() == o_r.tobytes()
+    assert ig.download().tobytes() == o_g.tobytes()
+    s = api.Seeds(ir, dr, ig, dg)
+    os_, nh, lim, histo = orc.merge_join(o_r, o_g, 64 << 30, hr.sizeof_db, hg.sizeof_db,
+                                         hr.maxlen, hr.nreads, hg.nreads)
+    assert s.count == nh and s.limit == lim
+    assert (s.histogram() == histo).all()
+    assert s.download().tobytes() == os_.tobytes()
+    # complement_DB on the device (damapper.c:433-469)
+    dg.complement()
+    n = int(hg.boff[-1]) + 1
+    assert (dg.download_bases()[:n] == rc[0][:n]).all()
+    # complemented index too
+    igc = api.Index(dg)
+    assert igc.download().tobytes() == orc.sort_kmers(orc.HostBlock(*rc), kmer, suppress).tobytes()
+
+
+def test_memory_cap_limit(api, oracle_mod):
+    """`limit` from -M (map.c:2992-3015), incl. -M0 = no cap."""
+    orc = oracle_mod
+    contigs, rb, rl, rd, rf, rc = make_case("C3", 0.002, 9)
+    hr, hg = api.HostBlock(*rd), api.HostBlock(*rf)
+    api.set_filter_params(12, 0, 4)
+    o_r = orc.sort_kmers(orc.HostBlock(*rd), 12)
+    o_g = orc.sort_kmers(orc.HostBlock(*rf), 12)
+    args = (hr.sizeof_db, hg.sizeof_db, hr.maxlen, hr.nreads, hg.nreads)
+    _, n_big, _, _ = orc.merge_join(o_r, o_g, 64 << 30, *args)
+    tight = hr.sizeof_db + hg.sizeof_db + 16 * (len(o_r) + len(o_g)) + 16 * (n_big // 2)
+    dr, dg = api.DeviceBlock(hr), api.DeviceBlock(hg)
+    ir, ig = api.Index(dr), api.Index(dg)
+    for mem in (tight, 0):
+        api.set_options(mem_limit=mem)
+        s = api.Seeds(ir, dr, ig, dg)
+        os_, nh, lim, _ = orc.merge_join(o_r, o_g, mem, *args)
+        assert (s.count, s.limit) == (nh, lim)
+        assert s.download().tobytes() == os_.tobytes()
+    api.set_options()
+
+
+def test_edge_cases(api, oracle_mod):
+    from damapper_b200 import dazzdb, las
+    orc = oracle_mod
+    rng = np.random.default_rng(1)
+    ref = [rng.integers(0, 4, 5000, dtype=np.uint8), rng.integers(0, 4, 333, dtype=np.uint8)]
+    rf = dazzdb.load_block(ref)
+    rc = dazzdb.load_block(dazzdb.revcomp_contigs(ref))
+
+    def both(reads, **kw):
+        rd = dazzdb.load_block(reads)
+        o = orc.map_block(orc.HostBlock(*rd), [(orc.HostBlock(*rf), orc.HostBlock(*rc))],
+                          orc.HostBlock(*rf), **kw)
+        g = api.map_block(api.HostBlock(*rd), [api.HostBlock(*rf)], api.HostBlock(*rf), **kw)
+        assert g["a"] == o["a"] and g["b"] == o["b"] and g["prof"] == o["prof"]
+        return g
+
+    # no shared k-mers at all: empty output
+    g = both([rng.integers(0, 4, 700, dtype=np.uint8) for _ in range(3)], do_b=1, profile=1)
+    assert g["a"] == b"" and g["b"] == b""
+    # exact copies, forward and reverse complement, ragged lengths down to exactly k
+    reads = [ref[0][1000:3000].copy(), (3 - ref[0][200:1500][::-1]).astype(np.uint8),
+             ref[0][4000:4020].copy(), ref[1].copy(), ref[0][0:61].copy()]
+    g = both(reads, do_b=1, profile=1)
+    recs = las.stream_records(g["a"], 100)
+    assert [r["diffs"] for r in recs] == [0] * len(recs) and len(recs) >= 3
+    assert recs[0]["flags"] == 0x14 and recs[1]["flags"] == 0x15
+    # a single read, a single contig, k-mers of length 32
+    both([ref[0][500:2500].copy()], kmer=32)
+
+
+def test_layer1_map_h_calls_write_las_files(api, oracle_mod, tmp_path):
+    """The four map.h entry points, called as damapper.c calls them, write per-thread .las files
+    whose concatenation is the oracle's record stream (T-invariant)."""
+    import ctypes as C
+    from damapper_b200 import dazzdb, las
+    orc = oracle_mod
+    contigs, rb, rl, rd, rf, rc = make_case("C5", 0.05, 41)
+    freq = base_freq(contigs)
+    o = orc.map_block(orc.HostBlock(*rd), [(orc.HostBlock(*rf), orc.HostBlock(*rc))],
+                      orc.HostBlock(*rf), freq=freq, do_b=1, profile=1)
+    L = api.load()
+    api.set_options(profile=1, sort_path=str(tmp_path))
+    assert L.damgpu_Set_Filter_Params(20, 0, 4) == 0
+    hr, hg, hc = api.HostBlock(*rd), api.HostBlock(*rf), api.HostBlock(*rc)
+    blen, alen = C.c_int(0), C.c_int(0)
+    bindex = L.damgpu_Sort_Kmers(C.byref(hr.c), C.byref(blen))
+    aindex = L.damgpu_Sort_Kmers(C.byref(hg.c), C.byref(alen))
+    L.damgpu_Match_Filter(C.byref(hr.c), C.byref(hg.c), bindex, blen, aindex, alen, 0, 1)
+    aindex = L.damgpu_Sort_Kmers(C.byref(hc.c), C.byref(alen))
+    L.damgpu_Match_Filter(C.byref(hr.c), C.byref(hc.c), bindex, blen, aindex, alen, 1, 0)
+    spec = api.CAlignSpec(0.85, 100, (C.c_float * 4)(*freq))
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        L.damgpu_Reporter(b"reads", C.byref(hr.c), b"ref", C.byref(hg.c), C.byref(spec), 3)
+    finally:
+        os.chdir(cwd)
+    L.damgpu_index_free(bindex)
+    m = [str(tmp_path / ("reads.ref.M%d.las" % i)) for i in range(1, 5)]
+    r = [str(tmp_path / ("ref.reads.R%d.las" % i)) for i in range(1, 5)]
+    assert las.canonical_stream(m) == o["a"]
+    assert las.canonical_stream(r) == o["b"]
+    assert open(tmp_path / ".reads.prof.data", "rb").read() == o["prof"]
+    anno = np.fromfile(tmp_path / ".reads.prof.anno", dtype=np.uint8)
+    assert len(anno) == 8 + 8 * (hr.nreads + 1)
+
+
+def test_full_size_properties(api):
+    """BASELINE config 2 at full size (4.6 Mbp + 13.8 k reads): properties that do not need the
+    oracle -- sortedness of the index and of the seeds, k-mer count, histogram/limit consistency,
+    Check_Trace_Points on every record, every read mapped."""
+    from damapper_b200 import las
+    contigs, rb, rl, rd, rf, rc = make_case("C2", 1.0, 7)
+    api.set_filter_params(20, 0, 4)
+    api.set_options()
+    hr, hg = api.HostBlock(*rd), api.HostBlock(*rf)
+    dr, dg = api.DeviceBlock(hr), api.DeviceBlock(hg)
+    ir, ig = api.Index(dr), api.Index(dg)
+    assert len(ir) == int(hr.boff[-1]) - 20 * hr.nreads
+    idx = ir.download()
+    code = idx["code"][:-2]
+    assert (np.diff(code.astype(np.int64)) >= 0).all()
+    tie = np.diff(code.astype(np.int64)) == 0
+    key = idx["read"][:-2].astype(np.int64) * (1 << 32) + idx["rpos"][:-2]
+    assert (np.diff(key)[tie] > 0).all()                       # (code, read, rpos) order
+    assert idx["code"][-2] == 0xffffffffffffffff and idx["code"][-1] == 0
+    # the multiset of codes is that of a direct recount on a sample of reads
+    s = api.Seeds(ir, dr, ig, dg)
+    seeds = s.download()[:s.count]
+    skey = [seeds["apos"] - seeds["diag"], seeds["apos"], seeds["bread"], seeds["aread"]]
+    assert (np.lexsort(skey) == np.arange(s.count)).all()
+    assert s.limit == 10000 and s.count == int((np.arange(10000) * s.histogram()).sum())
+    del idx, seeds
+    s.free(); ig.free(); ir.free(); dg.free(); dr.free()
+    out = api.map_block(hr, [hg], hg, freq=base_freq(contigs), do_b=1)
+    ra = las.stream_records(out["a"], 100)
+    rb_ = las.stream_records(out["b"], 100)
+    assert las.check_trace_points(ra, 100) == 0 and las.check_trace_points(rb_, 100) == 0
+    mapped = {r["aread"] for r in ra}
+    assert len(mapped) >= 0.995 * hr.nreads
+    assert out["anrec"] == out["bnrec"] == len(ra)
+    assert out["stats"]["overflow_jobs"] == 0 or out["stats"]["overflow_jobs"] < 50
+
+
+def test_host_driver_cli(api, tmp_path):
+    """The C host driver (damapper_b200/damapper): reference command line, DAZZ_DB input read
+    by its own loader, per-thread .las + .prof output equal to the reference's golden stream."""
+    import shutil
+    import subprocess
+    from damapper_b200 import dazzdb, las
+    from oracle.make_golden import CASES
+    exe = os.path.join(ROOT, "damapper_b200", "damapper")
+    assert os.path.exists(exe), "host driver not built"
+    cfg, scale, seed, flags, kw = CASES["c5_cover_profile"]
+    contigs, rb, rl, rd, rf, rc = make_case(cfg, scale, seed)
+    g = np.load(os.path.join(GOLDEN, "c5_cover_profile.npz"))
+    wd = str(tmp_path)
+    dazzdb.write_db(os.path.join(wd, "ref.dam"), contigs, is_dam=True)
+    dazzdb.write_db(os.path.join(wd, "reads.db"), (rb, rl))
+    # LAsort/LAcat/LAmerge are DALIGNER programs the driver shells out to (as the reference
+    # does, damapper.c:893-911); stubs that keep the per-thread files stand in for them
+    bindir = os.path.join(wd, "bin")
+    keep = os.path.join(wd, "keep")
+    os.makedirs(bindir); os.makedirs(keep); os.makedirs(os.path.join(wd, "tmp"))
+    with open(os.path.join(bindir, "LAsort"), "w") as f:
+        f.write('#!/bin/bash\nfor a in "$@"; do case "$a" in -*) ;; *) pat="$a";; esac; done\n'
+                'for f in ${pat/@/[0-9]*}; do [ -e "$f" ] && cp "$f" "%s"/; done\nexit 0\n' % keep)
+    for n in ("LAcat", "LAmerge"):
+        with open(os.path.join(bindir, n), "w") as f:
+            f.write("#!/bin/bash\nexit 0\n")
+    for n in ("LAsort", "LAcat", "LAmerge"):
+        os.chmod(os.path.join(bindir, n), 0o755)
+    env = dict(os.environ)
+    env["PATH"] = bindir + os.pathsep + env["PATH"]
+    p = subprocess.run([exe, "-T4", "-P" + os.path.join(wd, "tmp")] + list(flags) + ["ref.dam", "reads.db"],
+                       cwd=wd, env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr
+    m = [os.path.join(keep, "reads.ref.M%d.las" % i) for i in range(1, 5)]
+    r = [os.path.join(keep, "ref.reads.R%d.las" % i) for i in range(1, 5)]
+    assert las.canonical_stream(m) == g["a"].tobytes()
+    assert las.canonical_stream(r) == g["b"].tobytes()
+    assert open(os.path.join(wd, ".reads.prof.data"), "rb").read() == g["prof"].tobytes()
+    # error behaviour of the reference CLI is kept
+    p = subprocess.run([exe, "-N", "ref.dam", "reads.db"], cwd=wd, env=env, capture_output=True, text=True)
+    assert p.returncode == 1 and "Cannot specify N flag without C also" in p.stderr
+    p = subprocess.run([exe, "-k33", "ref.dam", "reads.db"], cwd=wd, env=env, capture_output=True, text=True)
+    assert p.returncode == 1 and "K-mer length must be 32 or less" in p.stderr
