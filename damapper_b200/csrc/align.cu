@@ -79,6 +79,11 @@ __device__ int wave(const WaveMem &wm, const AlignSpecD &sp, const uint8_t *__re
 #define IX(k) ((k) & WM)
 
   int hgh = k0, low = k0, dif = 0, avail = 0, cur = 0;
+  // Register path: while the band (with its two new diagonals) spans at most 32 diagonals, lane
+  // (k & 31) keeps diagonal k's state in registers and neighbours are reached with shuffles.
+  int rV = SENT, rM = 0, rHA = 0, rHB = 0, rNA = 0, rNB = 0;
+  uint64_t rT = 0;
+  bool generic = false;
   int more = 1, aclip, bclip;
   int besta, besty, trima, trimy, trimd, trimha, trimhb;
   int morea, morey, mored, moreha, morehb, morem, lasta;
@@ -137,14 +142,14 @@ __device__ int wave(const WaveMem &wm, const AlignSpecD &sp, const uint8_t *__re
         trimha = ha;
         trimhb = hb;
       }
-    if (lane == 0)
-      { wm.V[0][IX(k)] = c; wm.T[0][IX(k)] = PATH_INT; wm.M[0][IX(k)] = PATH_LEN;
-        wm.HA[0][IX(k)] = ha; wm.HB[0][IX(k)] = hb; wm.NA[IX(k)] = na; wm.NB[IX(k)] = nb;
-      }
-    __syncwarp();
+    rV = c; rT = PATH_INT; rM = PATH_LEN; rHA = ha; rHB = hb; rNA = na; rNB = nb;
   }
 
   // boundary handling after a wave (align.c:558-583,848-875 / 1216-1241,1502-1529)
+#define GETM(k)  (generic ? wm.M[cur][IX(k)]  : __shfl_sync(0xffffffffu, rM, (k) & 31))
+#define GETV(k)  (generic ? wm.V[cur][IX(k)]  : __shfl_sync(0xffffffffu, rV, (k) & 31))
+#define GETHA(k) (generic ? wm.HA[cur][IX(k)] : __shfl_sync(0xffffffffu, rHA, (k) & 31))
+#define GETHB(k) (generic ? wm.HB[cur][IX(k)] : __shfl_sync(0xffffffffu, rHB, (k) & 31))
 #define CLIP_AFTER_WAVE(SETD)                                                                   \
   if (more == 0)                                                                                \
     { const int o_ = (DIR > 0) ? 0 : -1;                                                        \
@@ -153,19 +158,21 @@ __device__ int wave(const WaveMem &wm, const AlignSpecD &sp, const uint8_t *__re
       const bool aclipped = (DIR > 0) ? (hgh >= aclip) : (low <= aclip);                        \
       if (aclipped)                                                                             \
         { if (DIR > 0) hgh = aclip - 1; else low = aclip + 1;                                   \
-          if (morem <= wm.M[cur][IX(aclip)])                                                    \
-            { morem = wm.M[cur][IX(aclip)]; morea = wm.V[cur][IX(aclip)];                       \
+          const int m_ = GETM(aclip);                                                           \
+          if (morem <= m_)                                                                      \
+            { morem = m_; morea = GETV(aclip);                                                  \
               morey = (morea - aclip) / 2; SETD                                                 \
-              moreha = wm.HA[cur][IX(aclip)]; morehb = wm.HB[cur][IX(aclip)];                   \
+              moreha = GETHA(aclip); morehb = GETHB(aclip);                                     \
             }                                                                                   \
         }                                                                                       \
       const bool bclipped = (DIR > 0) ? (low <= bclip) : (hgh >= bclip);                        \
       if (bclipped)                                                                             \
         { if (DIR > 0) low = bclip + 1; else hgh = bclip - 1;                                   \
-          if (morem <= wm.M[cur][IX(bclip)])                                                    \
-            { morem = wm.M[cur][IX(bclip)]; morea = wm.V[cur][IX(bclip)];                       \
+          const int m_ = GETM(bclip);                                                           \
+          if (morem <= m_)                                                                      \
+            { morem = m_; morea = GETV(bclip);                                                  \
               morey = (morea - bclip) / 2; SETD                                                 \
-              moreha = wm.HA[cur][IX(bclip)]; morehb = wm.HB[cur][IX(bclip)];                   \
+              moreha = GETHA(bclip); morehb = GETHB(bclip);                                     \
             }                                                                                   \
         }                                                                                       \
       aclip = (DIR > 0) ? IMAX : -IMAX;                                                         \
@@ -174,8 +181,194 @@ __device__ int wave(const WaveMem &wm, const AlignSpecD &sp, const uint8_t *__re
 
   CLIP_AFTER_WAVE(;)
 
-  // ---- successive waves (align.c:592-898 / 1248-1552)
+  // ---- successive waves, register path (align.c:592-898 / 1248-1552)
   while (more && GE<DIR>(lasta, besta - DIR * TRIM_MLAG))
+    { if (hgh < low)                    // empty band: the reference would read stale cells; stop
+        { st.empty += 1;
+          break;
+        }
+      if (hgh - low + 3 > 32)           // band outgrows the warp: continue in the window arrays
+        { const int k = low + ((lane - low) & 31);
+          if (k <= hgh)
+            { wm.V[0][IX(k)] = rV; wm.T[0][IX(k)] = rT; wm.M[0][IX(k)] = rM;
+              wm.HA[0][IX(k)] = rHA; wm.HB[0][IX(k)] = rHB; wm.NA[IX(k)] = rNA; wm.NB[IX(k)] = rNB;
+            }
+          __syncwarp();
+          cur = 0;
+          generic = true;
+          break;
+        }
+      low -= 1;
+      hgh += 1;
+      dif += 1;
+      const int  base = low;                           // diagonal of rotated-ballot bit 0
+      const int  width = hgh - low + 1;
+      const int  k = low + ((lane - low) & 31);
+      const bool act = (k <= hgh);
+      const int  lup = (lane + 1) & 31, ldn = (lane + 31) & 31;
+
+      // new outer diagonals inherit NA/NB from their inner neighbour (align.c:678-690)
+      { const int nau = __shfl_sync(0xffffffffu, rNA, lup), nbu = __shfl_sync(0xffffffffu, rNB, lup);
+        const int nad = __shfl_sync(0xffffffffu, rNA, ldn), nbd = __shfl_sync(0xffffffffu, rNB, ldn);
+        if (act && k == low) { rNA = nau; rNB = nbu; }
+        if (act && k == hgh) { rNA = nad; rNB = nbd; }
+      }
+      const int vold = (act && k > low && k < hgh) ? rV : SENT;
+      const int lp = (DIR > 0) ? lup : ldn, ln = (DIR > 0) ? ldn : lup;   // lanes of k+DIR, k-DIR
+      int vp = __shfl_sync(0xffffffffu, vold, lp);
+      int vn = __shfl_sync(0xffffffffu, vold, ln);
+      { const int kp = k + DIR, kn = k - DIR;
+        if (kp < low || kp > hgh) vp = SENT;
+        if (kn < low || kn > hgh) vn = SENT;
+      }
+      int c, srcl;
+      if (LT<DIR>(vold, vn))                            // align.c:712-741 / 1367-1396
+        { if (LT<DIR>(vn, vp)) { c = vp + DIR; srcl = lp; }
+          else                 { c = vn + DIR; srcl = ln; }
+        }
+      else
+        { if (LT<DIR>(vold, vp)) { c = vp + DIR; srcl = lp; }
+          else                   { c = vold + 2 * DIR; srcl = lane; }
+        }
+      int m  = __shfl_sync(0xffffffffu, rM, srcl);
+      int ha = __shfl_sync(0xffffffffu, rHA, srcl);
+      int hb = __shfl_sync(0xffffffffu, rHB, srcl);
+      uint64_t b;
+      { const unsigned tl = __shfl_sync(0xffffffffu, (unsigned) rT, srcl);
+        const unsigned th = __shfl_sync(0xffffffffu, (unsigned) (rT >> 32), srcl);
+        b = ((uint64_t) th << 32) | tl;
+      }
+      int y = 0, hit = 0, cntA = 0, cntB = 0, skipA = 0, skipB = 0;
+      if (act)
+        { if ((b & PATH_TOP) != 0) m -= 1;
+          b <<= 1;
+          const int y0 = (c - k) >> 1;
+          y = slide<DIR>(aseq, bseq, k, y0, hit);
+          const int r = (DIR > 0) ? y - y0 : y0 - y;
+          if (r > 0)                                    // closed form of align.c:764-767
+            { const int rr = (r < 61) ? r : 61;
+              const uint64_t mask = ((1ull << rr) - 1) << (61 - rr);
+              m += rr - __popcll(b & mask);
+              b = (r >= 64) ? ~0ull : ((b << r) | ((1ull << r) - 1));
+            }
+          c = (y << 1) + k;
+          if (GE<DIR>(y + k, rNA))                      // align.c:771-793 / 1426-1448
+            { cntA = (DIR * (y + k - rNA)) / TS + 1;
+              const int d0 = DIR * (cells[ha].mark - rNA);
+              if (d0 >= 0)
+                skipA = (d0 / TS + 1 < cntA) ? d0 / TS + 1 : cntA;
+            }
+          if (GE<DIR>(y, rNB))                          // align.c:795-817 / 1449-1471
+            { cntB = (DIR * (y - rNB)) / TS + 1;
+              const int d0 = DIR * (cells[hb].mark - rNB);
+              if (d0 >= 0)
+                skipB = (d0 / TS + 1 < cntB) ? d0 / TS + 1 : cntB;
+            }
+        }
+      else
+        c = SENT;
+
+      const int need = (cntA - skipA) + (cntB - skipB);
+      if (__ballot_sync(0xffffffffu, need > 0))         // Pebble allocation (rare)
+        { int pre = need;
+          for (int o = 1; o < 32; o <<= 1)
+            { const int t = __shfl_up_sync(0xffffffffu, pre, o);
+              if (lane >= o) pre += t;
+            }
+          const int total = __shfl_sync(0xffffffffu, pre, 31);
+          if (avail + total > wm.cmax) return ERR_CELLS;
+          int idx = avail + pre - need;
+          for (int i = skipA; i < cntA; i++)
+            { cells[idx] = Pebble{ ha, k, dif, rNA + DIR * TS * i };
+              ha = idx++;
+            }
+          for (int i = skipB; i < cntB; i++)
+            { cells[idx] = Pebble{ hb, k, dif, rNB + DIR * TS * i };
+              hb = idx++;
+            }
+          avail += total;
+          __syncwarp();
+        }
+      if (act)
+        { rNA += DIR * TS * cntA; rNB += DIR * TS * cntB;
+          rV = c; rT = b; rM = m; rHA = ha; rHB = hb;
+        }
+
+#define ROT(x)      __funnelshift_r((x), (x), base & 31)           /* bit i <-> diagonal base+i */
+#define LAST_SCAN(x)  ((DIR > 0) ? __ffs(x) - 1 : 31 - __clz(x))    /* last in scan order */
+#define FIRST_SCAN(x) ((DIR > 0) ? 31 - __clz(x) : __ffs(x) - 1)
+      // record breakers in scan order (align.c:819-833 / 1473-1487): prefix maximum along the
+      // scan direction over the circular lane layout
+      { const int cv = act ? ((DIR > 0) ? c : -c) : -IMAX;
+        int pm = cv;
+        for (int o = 1; o < width; o <<= 1)
+          { const int t = __shfl_sync(0xffffffffu, pm, (lane + DIR * o) & 31);
+            const bool ok = (DIR > 0) ? (k + o <= hgh) : (k - o >= low);
+            if (act && ok && t > pm) pm = t;
+          }
+        int before = __shfl_sync(0xffffffffu, pm, lp);
+        const int  bv = (DIR > 0) ? besta : -besta;
+        const bool hasprev = (DIR > 0) ? (k + 1 <= hgh) : (k - 1 >= low);
+        if (!hasprev || before < bv) before = bv;
+        const bool brk = act && (cv > before);
+        const unsigned bm = __ballot_sync(0xffffffffu, brk);
+        if (bm)
+          { const bool good = brk && (m >= PATH_AVE);
+            bool trim = false;
+            if (good)
+              { const int lo15 = (int) (b & TRIM_MASK), hi15 = (int) ((b >> TRIM_LEN) & TRIM_MASK);
+                if (__ldg(sp.table + lo15) >= 0)
+                  if (__ldg(sp.table + hi15) + __ldg(sp.score + lo15) >= 0)
+                    trim = true;
+              }
+            const unsigned gm = __ballot_sync(0xffffffffu, good);
+            const unsigned tm = __ballot_sync(0xffffffffu, trim);
+            const int lb = (base + LAST_SCAN(ROT(bm))) & 31;
+            besta = __shfl_sync(0xffffffffu, c, lb);
+            besty = __shfl_sync(0xffffffffu, y, lb);
+            if (gm)
+              lasta = __shfl_sync(0xffffffffu, c, (base + LAST_SCAN(ROT(gm))) & 31);
+            if (tm)
+              { const int lt = (base + LAST_SCAN(ROT(tm))) & 31;
+                trima  = __shfl_sync(0xffffffffu, c, lt);
+                trimy  = __shfl_sync(0xffffffffu, y, lt);
+                trimha = __shfl_sync(0xffffffffu, ha, lt);
+                trimhb = __shfl_sync(0xffffffffu, hb, lt);
+                trimd  = dif;
+              }
+          }
+      }
+      { const unsigned am = __ballot_sync(0xffffffffu, act && hit == 2);
+        const unsigned bb = __ballot_sync(0xffffffffu, act && hit == 1);
+        if (am | bb)
+          { more = 0;
+            if (am) aclip = base + LAST_SCAN(ROT(am));        // last writer in scan order
+            if (bb) bclip = base + FIRST_SCAN(ROT(bb));       // extreme k towards the scan start
+          }
+      }
+
+      CLIP_AFTER_WAVE(mored = dif;)
+
+      // trim the band to within WAVE_LAG of the best point (align.c:877-885 / 1531-1539)
+      { const int n = besta - DIR * WAVE_LAG;
+        const unsigned g = __ballot_sync(0xffffffffu, act && k >= low && k <= hgh && !LT<DIR>(rV, n));
+        if (g)
+          { const unsigned rg = ROT(g);
+            low = base + __ffs(rg) - 1;
+            hgh = base + 31 - __clz(rg);
+          }
+        else
+          hgh = low - 1;
+      }
+      st.nwaves += 1;
+      st.ncells += (hgh - low) + 1;
+    }
+#undef ROT
+#undef LAST_SCAN
+#undef FIRST_SCAN
+
+  // ---- successive waves, window path (band wider than the warp)
+  while (generic && more && GE<DIR>(lasta, besta - DIR * TRIM_MLAG))
     { if (hgh < low)                    // empty band: the reference would read stale cells; stop
         { st.empty += 1;
           break;
@@ -344,6 +537,10 @@ __device__ int wave(const WaveMem &wm, const AlignSpecD &sp, const uint8_t *__re
       st.ncells += (hgh - low) + 1;
     }
 #undef CLIP_AFTER_WAVE
+#undef GETM
+#undef GETV
+#undef GETHA
+#undef GETHB
 
   // ---- unwind the Pebble chains into trace pairs (align.c:900-1007 / 1554-1717), lane 0
   __syncwarp();

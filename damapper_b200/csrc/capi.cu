@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include <math.h>
+#include <time.h>
 #include <string>
 #include "../../include/libdamgpu.h"
 #include "common.cuh"
@@ -10,6 +11,8 @@
 #include "mapper.cuh"
 #include "report.cuh"
 #include <vector>
+#include <map>
+#include <unordered_map>
 
 namespace damgpu {
 
@@ -22,6 +25,18 @@ static bool        g_ready = false;
 static float       g_sort_times[3] = { 0, 0, 0 };
 
 Params g_par;          // filter parameters + the map.h globals
+bool   g_trace = false;
+
+void trace_mark(const char *name)
+{ static double last = 0;
+  cudaDeviceSynchronize();
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  const double now = ts.tv_sec * 1e3 + ts.tv_nsec / 1e6;
+  if (name != nullptr && last != 0)
+    fprintf(stderr, "[trace] %-28s %8.3f ms\n", name, now - last);
+  last = now;
+}
 
 void fatal(const char *fmt, ...)
 { char buf[1024];
@@ -38,6 +53,55 @@ void fatal(const char *fmt, ...)
 }
 
 int sm_count() { return g_sms > 0 ? g_sms : 148; }
+
+// ---- caching device allocator -----------------------------------------------------------
+static std::multimap<size_t, void *> g_free_blocks;      // size -> block
+static std::unordered_map<void *, size_t> g_block_size;  // every block ever handed out
+static size_t g_cached_bytes = 0;
+
+static size_t round_size(size_t b)
+{ if (b < (1u << 20)) return (b + 511) & ~(size_t) 511;
+  if (b < (64u << 20)) return (b + (1u << 20) - 1) & ~(size_t) ((1u << 20) - 1);
+  size_t step = 1;                                        // 1/16 of the enclosing power of two
+  while ((step << 5) <= b) step <<= 1;
+  return (b + step - 1) & ~(step - 1);
+}
+
+void *cache_alloc(size_t bytes)
+{ const size_t want = round_size(bytes);
+  auto it = g_free_blocks.lower_bound(want);
+  if (it != g_free_blocks.end() && it->first <= want + want / 4)
+    { void *p = it->second;
+      g_cached_bytes -= it->first;
+      g_free_blocks.erase(it);
+      return p;
+    }
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess)                                   // give cached memory back and retry
+    { cudaGetLastError();
+      cudaDeviceSynchronize();
+      for (auto &kv : g_free_blocks)
+        { cudaFree(kv.second);
+          g_block_size.erase(kv.second);
+        }
+      g_free_blocks.clear();
+      g_cached_bytes = 0;
+      e = cudaMalloc(&p, want);
+    }
+  if (e != cudaSuccess)
+    fatal("out of device memory allocating %zu bytes (%s)", want, cudaGetErrorString(e));
+  g_block_size[p] = want;
+  return p;
+}
+
+void cache_free(void *p)
+{ auto it = g_block_size.find(p);
+  if (it == g_block_size.end())
+    fatal("cache_free: unknown device pointer");
+  g_free_blocks.emplace(it->second, p);
+  g_cached_bytes += it->second;
+}
 
 static void need_gpu()
 { if (!g_ready)
@@ -78,11 +142,7 @@ int damgpu_init(int device)
       return 1;
     }
   g_sms = prop.multiProcessorCount;
-  { cudaMemPool_t pool;                                   // keep freed blocks in the pool
-    unsigned long long keep = ~0ull;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-  }
+  g_trace = (getenv("DAMGPU_TRACE") != nullptr);
   g_ready = true;
   return 0;
 }

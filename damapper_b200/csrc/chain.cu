@@ -15,20 +15,123 @@ namespace damgpu {
 constexpr int HITMIN = 3, MAX_GAP = 1000, MIN_PIECE = 300;   // map.c:34-37
 
 struct ChainScratch                 // one slot per seed
-{ int *from, *orig, *cost, *dead, *S, *E; };
+{ int *from, *orig, *cost, *dead, *E;
+  int4 *S;                          // spill area of the active set (node, diag, apos, -)
+};
 
-__device__ __forceinline__ int seed_apos(const SeedPair &h) { return h.apos + 1; }   // map.c:1784
+constexpr int CH_WARPS = 8;         // reads per CTA
+constexpr int CH_SCAP  = 128;       // active-set entries kept in shared memory per warp
 
-__global__ void __launch_bounds__(64)
+// remove the entry with key (d,a) from the sorted active set; all lanes, uniform
+__device__ __forceinline__ void set_remove(int4 *S, int &ns, int d, int a, int lane)
+{ int idx = -1;
+  for (int base = 0; base < ns && idx < 0; base += 32)
+    { const int j = base + lane;
+      int4 e = (j < ns) ? S[j] : make_int4(-1, 0, 0, 0);
+      const unsigned b = __ballot_sync(0xffffffffu, j < ns && e.y == d && e.z == a);
+      if (b) idx = base + __ffs(b) - 1;
+    }
+  if (idx < 0) return;
+  for (int base = idx; base < ns - 1; base += 32)
+    { const int j = base + lane;
+      int4 v = make_int4(0, 0, 0, 0);
+      if (j + 1 < ns) v = S[j + 1];
+      __syncwarp();
+      if (j < ns - 1) S[j] = v;
+      __syncwarp();
+    }
+  ns -= 1;
+}
+
+// Candidate test + dominance filter + Jump list for chain end h (map.c:1642-1767); one lane
+__device__ void consider(const SeedPair *__restrict__ hits, int64_t g0, int h, int ar, int br,
+                         int comp, int K, int profile, int spacing, int *from, const int *orig,
+                         const int *cost, Candidate *cand, int *cand_top, int cand_cap,
+                         uint32_t *jumps, unsigned long long *jump_top, unsigned long long jump_cap,
+                         int &chead, int16_t *cover, const int64_t *coff, int *overflow)
+{
+#define APOS(n) (hits[g0 + (n)].apos + 1)
+#define BPOS(n) (hits[g0 + (n)].apos + 1 - hits[g0 + (n)].diag)
+  const int ab = APOS(orig[h]) - K, bb = BPOS(orig[h]) - K;
+  const int ae = APOS(h), be = BPOS(h);
+  const int hc = cost[h];
+
+  if (profile)                                  // map.c:1654-1666
+    { int16_t *cnt = cover + coff[ar];
+      const int tb = ab / spacing, te = (ae - 1) / spacing + 1;
+      const int cb = cnt[tb], ce = cnt[te];
+      if (cb < 0x7fff && ce > -0xffff)
+        { cnt[tb] = (int16_t) (cb + 1);
+          cnt[te] = (int16_t) (ce - 1);
+        }
+    }
+
+  int c = -1, d, e;                             // dominance filter, map.c:1675-1713
+  for (d = chead; d >= 0; d = e)
+    { Candidate *D = cand + d;
+      const bool A = (D->afirst < ab + MIN_PIECE && D->alast > ae - MIN_PIECE);
+      const bool B = (ab < D->afirst + MIN_PIECE && ae > D->alast - MIN_PIECE);
+      e = D->next;
+      if (A && .9 * (double) D->score >= (double) hc)
+        break;
+      if (B && (double) D->score <= .9 * (double) hc)
+        { if (c < 0) chead = e; else cand[c].next = e;
+          D->next = -2;
+        }
+      else
+        c = d;
+    }
+  if (d >= 0)
+    return;
+
+  d = atomicAdd(cand_top, 1);
+  if (d >= cand_cap) { *overflow = 1; return; }
+  Candidate *D = cand + d;
+  D->next = chead; chead = d;
+  D->bread = br; D->comp = comp; D->score = hc;
+  D->afirst = ab; D->alast = ae; D->bfirst = bb; D->blast = be;
+
+  int len = 0;                                  // chain_length, map.c:1243-1260 (splices persist)
+  { int x = h, y = from[h];
+    while (y >= 0)
+      { const int da = APOS(x) - APOS(y);
+        if (da == BPOS(x) - BPOS(y) && da < 100)
+          y = from[x] = from[y];
+        else
+          { len += 1; x = y; y = from[x]; }
+      }
+  }
+  D->length = len;
+  unsigned long long jo = 0;
+  if (len > 0)
+    { jo = atomicAdd(jump_top, (unsigned long long) len);
+      if (jo + len > jump_cap) { *overflow = 1; return; }
+      int g = h, k = 0;
+      for (int f = from[h]; f >= 0; f = from[f])          // map.c:1746-1759
+        { const uint32_t da = (uint16_t) (APOS(g) - APOS(f));
+          const uint32_t db = (uint16_t) (BPOS(g) - BPOS(f));
+          jumps[jo + k++] = da | (db << 16);
+          g = f;
+        }
+    }
+  D->chain = (long long) jo;
+#undef APOS
+#undef BPOS
+}
+
+// One warp per read.  The lanes scan the sorted active set 32 entries at a time (insert position,
+// predOf/leftmost, succOf, removals); everything else is warp-uniform scalar work.
+__global__ void __launch_bounds__(CH_WARPS * 32)
 k_chain(const SeedPair *__restrict__ hits, int64_t nhits, int nreads, int K, int bstart, int comp,
         int profile, int spacing, ChainScratch sc, Candidate *cand, int *cand_top, int cand_cap,
         uint32_t *jumps, unsigned long long *jump_top, unsigned long long jump_cap,
         int *head, int16_t *cover, const int64_t *__restrict__ coff, int *overflow)
-{ const int ar = blockIdx.x * blockDim.x + threadIdx.x;
+{ __shared__ int4 s_S[CH_WARPS][CH_SCAP];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ar = blockIdx.x * CH_WARPS + warp;
   if (ar >= nreads) return;
 
-  // seed range of read ar (hits are sorted by aread first)
-  int64_t lo = 0, hi = nhits;
+  int64_t lo = 0, hi = nhits;                        // seed range of read ar
   while (lo < hi)
     { int64_t mid = (lo + hi) >> 1;
       if (hits[mid].aread < ar) lo = mid + 1; else hi = mid;
@@ -43,63 +146,106 @@ k_chain(const SeedPair *__restrict__ hits, int64_t nhits, int nreads, int K, int
     { const int     br = hits[nidx].bread;
       const int64_t g0 = nidx;                         // group base: node n <-> seed g0+n
       int *from = sc.from + g0, *orig = sc.orig + g0, *cost = sc.cost + g0, *dead = sc.dead + g0;
-      int *S = sc.S + g0, *E = sc.E + g0;
+      int *E = sc.E + g0;
+      int4 *S = s_S[warp];
+      bool spilled = false;
       int nn = 0, ns = 0, nexp = 0, qhead = 0;
 
-#define APOS(n) (hits[g0 + (n)].apos + 1)
-#define DIAG(n) (hits[g0 + (n)].diag)
-#define BPOS(n) (APOS(n) - DIAG(n))
-
-      for ( ; nidx < nhits && hits[nidx].aread == ar && hits[nidx].bread == br; nidx++)
-        { const int apos = hits[nidx].apos + 1;
-          const int diag = hits[nidx].diag;
+      for ( ; nidx < nhits; nidx++)
+        { const SeedPair hp = hits[nidx];
+          if (hp.aread != ar || hp.bread != br) break;
+          const int apos = hp.apos + 1;
+          const int diag = hp.diag;
           const int bpos = apos - diag;
-          int pos, l, r, lcost, rcost, j;
 
-          while (qhead < nn && APOS(qhead) < apos - MAX_GAP)       // map.c:1787-1796
+          while (qhead < nn && hits[g0 + qhead].apos + 1 < apos - MAX_GAP)   // map.c:1787-1796
             { const int q = qhead++;
               if (!dead[q])
-                { for (j = 0; j < ns; j++)
-                    if (S[j] == q) break;
-                  for ( ; j < ns - 1; j++) S[j] = S[j + 1];
-                  ns -= 1;
+                { set_remove(S, ns, hits[g0 + q].diag, hits[g0 + q].apos + 1, lane);
                   if (orig[orig[q]] == q)
-                    E[nexp++] = q;
+                    { if (lane == 0) E[nexp] = q;
+                      nexp += 1;
+                    }
                 }
             }
 
           const int n = nn++;
-          dead[n] = 0;
-          for (pos = 0; pos < ns; pos++)              // key: diag desc, apos desc (map.c:1101)
-            { const int x = S[pos];
-              const int xd = DIAG(x);
-              if (diag > xd || (diag == xd && apos > APOS(x)))
-                break;
+          if (!spilled && ns + 1 > CH_SCAP)            // active set outgrew shared memory
+            { int4 *G = sc.S + g0;
+              for (int j = lane; j < ns; j += 32) G[j] = S[j];
+              __syncwarp();
+              S = G; spilled = true;
             }
-          for (j = ns; j > pos; j--) S[j] = S[j - 1];
-          S[pos] = n;
+
+          // insert position: key order diag desc, apos desc (add, map.c:1101)
+          int pos = ns;
+          for (int base = 0; base < ns; base += 32)
+            { const int j = base + lane;
+              int4 e = (j < ns) ? S[j] : make_int4(0, 0, 0, 0);
+              const unsigned b = __ballot_sync(0xffffffffu,
+                                               j < ns && (diag > e.y || (diag == e.y && apos > e.z)));
+              if (b) { pos = base + __ffs(b) - 1; break; }
+            }
+          for (int top = ns; top > pos; top -= 32)     // shift right, top chunk first
+            { const int j = top - 1 - lane;
+              int4 v = make_int4(0, 0, 0, 0);
+              if (j >= pos) v = S[j];
+              __syncwarp();
+              if (j >= pos) S[j + 1] = v;
+              __syncwarp();
+            }
+          if (lane == 0) S[pos] = make_int4(n, diag, apos, 0);
+          __syncwarp();
           ns += 1;
 
-          l = -1;                                     // predOf + leftmost, map.c:1806-1808
-          for (j = pos - 1; j >= 0; j--)
-            if (BPOS(S[j]) >= bpos - MAX_GAP)
-              { l = S[j];
-                while (j > 0 && DIAG(S[j - 1]) == DIAG(l))
-                  l = S[--j];
-                break;
-              }
-          r = -1;                                     // succOf, map.c:1809
-          for (j = pos + 1; j < ns; j++)
-            if (BPOS(S[j]) <= bpos)
-              { r = S[j];
-                break;
-              }
-
-          lcost = rcost = 0;                          // map.c:1810-1826
+          // predOf + leftmost (map.c:1806-1808): nearest predecessor with bpos' >= bpos-MAX_GAP,
+          // replaced by the max-apos node on its diagonal
+          int l = -1, lj = -1, ld = 0, la = 0;
+          for (int base = pos - 1; base >= 0 && l < 0; base -= 32)
+            { const int j = base - lane;
+              int4 e = (j >= 0) ? S[j] : make_int4(0, 0, 0, 0);
+              const unsigned b = __ballot_sync(0xffffffffu, j >= 0 && (e.z - e.y) >= bpos - MAX_GAP);
+              if (b)
+                { const int src = __ffs(b) - 1;
+                  lj = base - src;
+                  l  = __shfl_sync(0xffffffffu, e.x, src);
+                  ld = __shfl_sync(0xffffffffu, e.y, src);
+                  la = __shfl_sync(0xffffffffu, e.z, src);
+                }
+            }
           if (l >= 0)
-            lcost = cost[l] + ((apos >= APOS(l) + K) ? K : apos - APOS(l));
+            for (int base = lj - 1; base >= 0; base -= 32)
+              { const int j = base - lane;
+                int4 e = (j >= 0) ? S[j] : make_int4(0, 0, 0, 0);
+                const unsigned b = __ballot_sync(0xffffffffu, j >= 0 && e.y == ld);
+                const int run = (b == 0xffffffffu) ? 32 : __ffs(~b) - 1;
+                if (run > 0)
+                  { l  = __shfl_sync(0xffffffffu, e.x, run - 1);
+                    la = __shfl_sync(0xffffffffu, e.z, run - 1);
+                  }
+                if (run < 32) break;
+              }
+          // succOf (map.c:1809): nearest successor with bpos' <= bpos
+          int r = -1, rd = 0, ra = 0;
+          for (int base = pos + 1; base < ns && r < 0; base += 32)
+            { const int j = base + lane;
+              int4 e = (j < ns) ? S[j] : make_int4(0, 0, 0, 0);
+              const unsigned b = __ballot_sync(0xffffffffu, j < ns && (e.z - e.y) <= bpos);
+              if (b)
+                { const int src = __ffs(b) - 1;
+                  r  = __shfl_sync(0xffffffffu, e.x, src);
+                  rd = __shfl_sync(0xffffffffu, e.y, src);
+                  ra = __shfl_sync(0xffffffffu, e.z, src);
+                }
+            }
+
+          int lcost = 0, rcost = 0;                   // map.c:1810-1826
+          if (l >= 0)
+            lcost = cost[l] + ((apos >= la + K) ? K : apos - la);
           if (r >= 0)
-            rcost = cost[r] + ((bpos >= BPOS(r) + K) ? K : bpos - BPOS(r));
+            { const int rb = ra - rd;
+              rcost = cost[r] + ((bpos >= rb + K) ? K : bpos - rb);
+            }
           if (lcost > rcost)
             rcost = 0;
           else
@@ -108,106 +254,48 @@ k_chain(const SeedPair *__restrict__ hits, int64_t nhits, int nreads, int K, int
           if (lcost > 0 || rcost > 0)                 // map.c:1828-1857
             { const int p = (lcost > 0) ? l : r;
               const int c = (lcost > 0) ? lcost : rcost;
-              from[n] = p;
-              cost[n] = c;
+              const int pd = (lcost > 0) ? ld : rd, pa = (lcost > 0) ? la : ra;
               const int o = (from[p] < 0) ? p : orig[p];
-              orig[n] = o;
-              if (c >= cost[orig[o]])
-                { int dd = DIAG(p) - diag;
-                  orig[o] = n;
+              const bool best = (c >= cost[orig[o]]);
+              __syncwarp();
+              if (lane == 0)
+                { from[n] = p; cost[n] = c; orig[n] = o; dead[n] = 0;
+                  if (best) orig[o] = n;
+                }
+              __syncwarp();
+              if (best)
+                { int dd = pd - diag;
                   if (dd < 0) dd = -dd;
-                  if ((double) dd <= .2 * (double) (apos - APOS(p)))
-                    { for (j = 0; j < ns; j++)
-                        if (S[j] == p) break;
-                      for ( ; j < ns - 1; j++) S[j] = S[j + 1];
-                      ns -= 1;
-                      dead[p] = 1;
+                  if ((double) dd <= .2 * (double) (apos - pa))
+                    { set_remove(S, ns, pd, pa, lane);
+                      if (lane == 0) dead[p] = 1;
+                      __syncwarp();
                     }
                 }
             }
           else
-            { from[n] = -1;
-              cost[n] = K;
-              orig[n] = n;
+            { if (lane == 0)
+                { from[n] = -1; cost[n] = K; orig[n] = n; dead[n] = 0; }
+              __syncwarp();
             }
         }
 
       // candidates of the group: live set in key order, then expired (newest first), map.c:1634-1767
-      for (int pass = 0; pass < 2; pass++)
-        for (int jj = 0; jj < (pass == 0 ? ns : nexp); jj++)
-          { const int h = (pass == 0) ? S[jj] : E[nexp - 1 - jj];
-            if (!(cost[h] >= hithr && orig[orig[h]] == h))
-              continue;
-            const int ab = APOS(orig[h]) - K, bb = BPOS(orig[h]) - K;
-            const int ae = APOS(h), be = BPOS(h);
-            const int hc = cost[h];
-
-            if (profile)                              // map.c:1654-1666
-              { int16_t *cnt = cover + coff[ar];
-                const int tb = ab / spacing, te = (ae - 1) / spacing + 1;
-                const int cb = cnt[tb], ce = cnt[te];
-                if (cb < 0x7fff && ce > -0xffff)
-                  { cnt[tb] = (int16_t) (cb + 1);
-                    cnt[te] = (int16_t) (ce - 1);
-                  }
+      __syncwarp();
+      if (lane == 0)
+        { for (int pass = 0; pass < 2; pass++)
+            for (int jj = 0; jj < (pass == 0 ? ns : nexp); jj++)
+              { const int h = (pass == 0) ? S[jj].x : E[nexp - 1 - jj];
+                if (cost[h] >= hithr && orig[orig[h]] == h)
+                  consider(hits, g0, h, ar, br + bstart, comp, K, profile, spacing, from, orig, cost,
+                           cand, cand_top, cand_cap, jumps, jump_top, jump_cap, chead, cover, coff,
+                           overflow);
               }
-
-            int c = -1, d, e;                         // dominance filter, map.c:1675-1713
-            for (d = chead; d >= 0; d = e)
-              { Candidate *D = cand + d;
-                const bool A = (D->afirst < ab + MIN_PIECE && D->alast > ae - MIN_PIECE);
-                const bool B = (ab < D->afirst + MIN_PIECE && ae > D->alast - MIN_PIECE);
-                e = D->next;
-                if (A && .9 * (double) D->score >= (double) hc)
-                  break;
-                if (B && (double) D->score <= .9 * (double) hc)
-                  { if (c < 0) chead = e; else cand[c].next = e;
-                    D->next = -2;
-                  }
-                else
-                  c = d;
-              }
-            if (d >= 0)
-              continue;
-
-            d = atomicAdd(cand_top, 1);
-            if (d >= cand_cap) { *overflow = 1; return; }
-            Candidate *D = cand + d;
-            D->next = chead; chead = d;
-            D->bread = br + bstart; D->comp = comp; D->score = hc;
-            D->afirst = ab; D->alast = ae; D->bfirst = bb; D->blast = be;
-
-            // chain_length, map.c:1243-1260 (the splices persist)
-            int len = 0;
-            { int x = h, y = from[h];
-              while (y >= 0)
-                { const int da = APOS(x) - APOS(y);
-                  if (da == BPOS(x) - BPOS(y) && da < 100)
-                    y = from[x] = from[y];
-                  else
-                    { len += 1; x = y; y = from[x]; }
-                }
-            }
-            D->length = len;
-            unsigned long long jo = 0;
-            if (len > 0)
-              { jo = atomicAdd(jump_top, (unsigned long long) len);
-                if (jo + len > jump_cap) { *overflow = 1; return; }
-                int g = h, k = 0;
-                for (int f = from[h]; f >= 0; f = from[f])          // map.c:1746-1759
-                  { const uint32_t da = (uint16_t) (APOS(g) - APOS(f));
-                    const uint32_t db = (uint16_t) (BPOS(g) - BPOS(f));
-                    jumps[jo + k++] = da | (db << 16);
-                    g = f;
-                  }
-              }
-            D->chain = (long long) jo;
-          }
-#undef APOS
-#undef DIAG
-#undef BPOS
+        }
+      chead = __shfl_sync(0xffffffffu, chead, 0);
+      __syncwarp();
     }
-  head[ar] = chead;
+  if (lane == 0) head[ar] = chead;
 }
 
 static void ensure_pools(Mapper *m, int64_t nhits)
@@ -284,19 +372,23 @@ void chain_seeds(Mapper *m, const SeedSet *ss, int bstart, int comp, cudaStream_
   if (nhits == 0) return;
   if (m->spacing != g_par.spacing)
     fatal("SPACING changed after the mapper was created");
+  TRACE(nullptr);
   ensure_pools(m, nhits);
+  TRACE("chain: ensure_pools");
   ChainScratch sc;
-  int *scratch = dalloc<int>((size_t) nhits * 6);
+  int *scratch = dalloc<int>((size_t) nhits * 5);
   sc.from = scratch; sc.orig = scratch + nhits; sc.cost = scratch + 2 * nhits;
-  sc.dead = scratch + 3 * nhits; sc.S = scratch + 4 * nhits; sc.E = scratch + 5 * nhits;
+  sc.dead = scratch + 3 * nhits; sc.E = scratch + 4 * nhits;
+  sc.S = dalloc<int4>((size_t) nhits);
   const int n = m->reads->nreads;
-  LAUNCH(k_chain, (n + 63) / 64, 64, 0, stream, ss->hits, nhits, n, g_par.kmer, bstart, comp,
+  LAUNCH(k_chain, (n + CH_WARPS - 1) / CH_WARPS, CH_WARPS * 32, 0, stream, ss->hits, nhits, n, g_par.kmer, bstart, comp,
          g_par.profile, g_par.spacing, sc, m->cand, m->cand_top, m->cand_cap, m->jumps,
          m->jump_top, (unsigned long long) m->jump_cap, m->head, m->cover, m->coff, m->overflow);
   int ovf = 0;
   CUDA_CHECK(cudaMemcpyAsync(&ovf, m->overflow, sizeof(int), cudaMemcpyDeviceToHost, stream));
   CUDA_CHECK(cudaStreamSynchronize(stream));
-  dfree(scratch);
+  dfree(scratch); dfree(sc.S);
+  TRACE("chain: kernel");
   if (ovf)
     fatal("Match_Filter: candidate/jump pool overflow (internal sizing error)");
 }

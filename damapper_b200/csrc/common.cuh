@@ -33,20 +33,27 @@ extern unsigned long long g_launches;
        KERNEL_CHECK();                                                \
   } while (0)
 
-// Device memory comes from the stream-ordered pool of the default stream (cudaMallocAsync) with
-// an unlimited release threshold: after the first step every buffer is recycled inside the
-// process instead of being mapped/unmapped by the driver (GB-sized cudaMalloc/cudaFree calls
-// cost more host time than the kernels that use them).
+// Device memory comes from a caching allocator owned by the library (capi.cu): freed blocks go
+// to size-keyed free lists and are handed out again for requests of (almost) the same size, so
+// after the first step no GB-sized cudaMalloc/cudaFree reaches the driver (those calls cost more
+// host time than the kernels using the buffers).  All work runs on one stream, so reuse is
+// stream-ordered.
+void *cache_alloc(size_t bytes);
+void  cache_free(void *p);
+
 template <typename T> static inline T *dalloc(size_t n)
-{ T *p = nullptr;
-  if (n == 0) n = 1;
-  CUDA_CHECK(cudaMallocAsync((void **) &p, n * sizeof(T), 0));
-  return p;
+{ if (n == 0) n = 1;
+  return static_cast<T *>(cache_alloc(n * sizeof(T)));
 }
 
-static inline void dfree(void *p) { if (p) CUDA_CHECK(cudaFreeAsync(p, 0)); }
+static inline void dfree(void *p) { if (p) cache_free(p); }
 
 int sm_count();
+
+// DAMGPU_TRACE=1: wall-clock per named phase (device synchronised at every mark), to stderr
+void trace_mark(const char *name);
+#define TRACE(name) do { if (damgpu::g_trace) damgpu::trace_mark(name); } while (0)
+extern bool g_trace;
 
 // ---- radix_sort.cu -------------------------------------------------------------------
 // Stable LSD radix sort of n 16-byte records on the key bytes listed in `bytes` (least

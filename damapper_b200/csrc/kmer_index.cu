@@ -255,25 +255,34 @@ DeviceBlock *upload_block(const uint8_t *bases, const int64_t *boff, const int32
   return blk;
 }
 
-// In-place reverse complement of every read (complement, damapper.c:417-431)
-__global__ void k_complement(uint8_t *bases, const int64_t *__restrict__ boff, int nreads)
-{ for (int r = blockIdx.x; r < nreads; r += gridDim.x)
-    { uint8_t *s = bases + boff[r];
-      const int len = (int) (boff[r + 1] - boff[r] - 1);
-      for (int i = threadIdx.x; i < (len + 1) / 2; i += blockDim.x)
-        { const int j = len - 1 - i;
-          const uint8_t a = s[i], b = s[j];
-          s[i] = (uint8_t) (3 - b);
-          s[j] = (uint8_t) (3 - a);
+// In-place reverse complement of every read (complement, damapper.c:417-431).  One thread per
+// base position of the first half of its read: position q of read r swaps with its mirror.
+__global__ void __launch_bounds__(256)
+k_complement(uint8_t *bases, const int64_t *__restrict__ boff, int nreads, int64_t total)
+{ for (int64_t q = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; q < total;
+       q += (int64_t) gridDim.x * blockDim.x)
+    { int lo = 0, hi = nreads - 1;                    // read holding position q
+      while (lo < hi)
+        { int mid = (lo + hi + 1) >> 1;
+          if (boff[mid] <= q) lo = mid; else hi = mid - 1;
         }
+      const int64_t b0 = boff[lo];
+      const int len = (int) (boff[lo + 1] - b0 - 1);
+      const int i = (int) (q - b0);
+      if (i >= (len + 1) / 2)
+        continue;                                     // second half or the terminator
+      const int j = len - 1 - i;
+      const uint8_t a = bases[b0 + i], b = bases[b0 + j];
+      bases[b0 + i] = (uint8_t) (3 - b);
+      bases[b0 + j] = (uint8_t) (3 - a);
     }
 }
 
 void complement_block(DeviceBlock *blk, cudaStream_t stream)
 { if (blk->nreads == 0) return;
-  int grid = blk->nreads < sm_count() * 8 ? blk->nreads : sm_count() * 8;
-  LAUNCH(k_complement, grid, 256, 0, stream, blk->bases, blk->boff, blk->nreads);
-  CUDA_CHECK(cudaStreamSynchronize(stream));
+  int64_t nb = (blk->total + 255) / 256;
+  int grid = nb < (int64_t) sm_count() * 16 ? (int) nb : sm_count() * 16;
+  LAUNCH(k_complement, grid, 256, 0, stream, blk->bases, blk->boff, blk->nreads, blk->total);
 }
 
 void free_block(DeviceBlock *blk)
@@ -301,6 +310,7 @@ KmerIndex *sort_kmers(const DeviceBlock *blk, int K, int suppress, cudaStream_t 
   for (int i = 0; i < 2 * K; i += 8)                   // mersort, map.c:670-673
     bytes[npass++] = i >> 3;
 
+  TRACE(nullptr);
   KmerPos  *a = dalloc<KmerPos>((size_t) n + 2);
   KmerPos  *b = dalloc<KmerPos>((size_t) n + 2);
   uint32_t *hist = dalloc<uint32_t>(256 * 16);
@@ -316,6 +326,7 @@ KmerIndex *sort_kmers(const DeviceBlock *blk, int K, int suppress, cudaStream_t 
     }
   LAUNCH(k_extract, grid, EX_THREADS, 0, stream, blk->bases, blk->boff, nreads, blk->total, K,
          npass, a, hist);
+  TRACE("sort_kmers: alloc+extract");
   if (g_time_kernels) cudaEventRecord(e1, stream);
   KmerPos *rez = (KmerPos *) radix_sort16(a, b, n, bytes, npass, hist, stream);
   if (g_time_kernels)
@@ -327,6 +338,7 @@ KmerIndex *sort_kmers(const DeviceBlock *blk, int K, int suppress, cudaStream_t 
       idx->ms_extract = t1; idx->ms_sort = t2; idx->npass = npass;
       cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     }
+  TRACE("sort_kmers: radix");
   KmerPos *other = (rez == a) ? b : a;
   dfree(hist);
 
@@ -351,6 +363,7 @@ KmerIndex *sort_kmers(const DeviceBlock *blk, int K, int suppress, cudaStream_t 
     }
   LAUNCH(k_set_sentinels, 1, 1, 0, stream, rez, (int64_t) kept);
   CUDA_CHECK(cudaStreamSynchronize(stream));
+  TRACE("sort_kmers: tail");
   idx->list = rez;
   idx->len  = (int) kept;
   return idx;

@@ -603,6 +603,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   if (m->spacing != S)
     fatal("SPACING changed after the mapper was created");
 
+  TRACE(nullptr);
   // alignment spec tables
   std::vector<int16_t> tables(65536);
   int ave_path = 0;
@@ -617,6 +618,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
                              cudaMemcpyDeviceToDevice, stream));
   complement_block(&rc, stream);
 
+  TRACE("report: spec+rc copy");
   // jobs = live candidates in (read, list order)
   int *d_cnt = dalloc<int>(n + 1);
   LAUNCH(k_count_cands, (n + 255) / 256, 256, 0, stream, m->head, m->cand, n, d_cnt);
@@ -631,6 +633,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   AlignJob *d_jobs = dalloc<AlignJob>((size_t) njobs + 1);
   LAUNCH(k_fill_jobs, (n + 255) / 256, 256, 0, stream, m->head, m->cand, n, d_job_off, d_jobs);
 
+  TRACE("report: jobs");
   // scratch + output pools of the alignment phase
   const int nblocks = std::min((njobs + ALIGN_WARPS - 1) / ALIGN_WARPS, sm_count() * 8);
   const int nwarps = std::max(1, nblocks) * ALIGN_WARPS;
@@ -666,6 +669,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   A.traces = d_traces; A.trace_top = d_ull; A.trace_cap = trace_cap;
   A.nfailed = d_ctr + 2; A.stats = d_ull + 1;
 
+  TRACE("report: alloc");
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_time_kernels)
     { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, stream); }
@@ -677,6 +681,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
       cudaEventDestroy(e0); cudaEventDestroy(e1);
     }
 
+  TRACE("report: align kernel");
   // re-run the jobs that outgrew the fast configuration / the output pools
   int *d_list = nullptr;
   for (int round = 0; ; round++)
@@ -721,6 +726,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   out->nalign = (int64_t) stats[1]; out->nwaves = (int64_t) stats[2]; out->ncells = (int64_t) stats[3];
   out->empty_band = (int64_t) stats[4];
 
+  TRACE("report: overflow loop");
   // per-read sizing of the second half
   int     *d_novl = dalloc<int>(n + 1);
   int64_t *d_asum = dalloc<int64_t>(n + 1), *d_bsum = dalloc<int64_t>(n + 1);
@@ -762,6 +768,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   R.prof = dalloc<uint8_t>((size_t) m->h_coff[n] + 1);
   for (int i = 0; i <= 40; i++) R.spow[i] = pow(10., i / 10.);       // map.c:2279-2280
   R.error = d_ctr + 4; R.h2_events = d_ull + 6;
+  TRACE("report: sizing+alloc");
   LAUNCH(k_report, (n + 63) / 64, 64, 0, stream, R);
   int rerr = 0;
   CUDA_CHECK(cudaMemcpyAsync(&rerr, d_ctr + 4, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -771,6 +778,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   if (rerr != 0)
     fatal("Reporter: internal buffer overflow (code %d)", rerr);
 
+  TRACE("report: k_report");
   // copy out and compact per read (record order = read order, as the per-thread files concatenate)
   { std::vector<uint8_t> ra = d2h(R.out_a, (size_t) ta);
     std::vector<int64_t> ua = d2h(R.used_a, n);
@@ -801,6 +809,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
     out->h2_events = (int64_t) d2h(d_ull + 6, 1)[0];
   }
 
+  TRACE("report: copy out");
   dfree(R.ftraces); dfree(R.amatch); dfree(R.tmp); dfree(R.bmatch); dfree(R.linker); dfree(R.perm);
   dfree(R.part); dfree(R.out_a); dfree(R.out_b); dfree(R.used_a); dfree(R.used_b);
   dfree(R.nrec_a); dfree(R.nrec_b); dfree(R.prof);
@@ -809,6 +818,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   dfree(d_alns); dfree(d_traces); dfree(d_list); dfree(d_big);
   dfree(d_cells); dfree(d_tscr); dfree(d_ctr); dfree(d_ull);
   dfree(d_jobs); dfree(d_job_off); dfree(d_cnt); dfree(rc.raw); dfree(d_tables);
+  TRACE("report: frees");
   return out;
 }
 

@@ -299,6 +299,7 @@ SeedSet *merge_join(const KmerIndex *aidx, const DeviceBlock *ablock, const Kmer
     return ss;
   const KmerPos *A = aidx->list, *B = bidx->list;
 
+  TRACE(nullptr);
   // prefix table: about 4 B records per bucket, at most 2^24 buckets
   int P = 1;
   while ((1ll << P) * 4 < blen && P < 24) P++;
@@ -319,6 +320,7 @@ SeedSet *merge_join(const KmerIndex *aidx, const DeviceBlock *ablock, const Kmer
   uint32_t nruns = 0;
   CUDA_CHECK(cudaMemcpyAsync(&nruns, counter + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
 
+  TRACE("join: lut+match launch");
   unsigned long long *gram = dalloc<unsigned long long>(MAXGRAM + 1);
   CUDA_CHECK(cudaMemsetAsync(gram, 0, sizeof(unsigned long long) * (MAXGRAM + 1), stream));
   CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -335,6 +337,7 @@ SeedSet *merge_join(const KmerIndex *aidx, const DeviceBlock *ablock, const Kmer
   CUDA_CHECK(cudaStreamSynchronize(stream));
   dfree(gram);
 
+  TRACE("join: match sync+histogram");
   const int limit = compute_limit(ss->histo.data(), mem_limit, ablock->sizeof_db,
                                   bblock->sizeof_db, alen, blen);
   ss->limit = limit;
@@ -357,6 +360,7 @@ SeedSet *merge_join(const KmerIndex *aidx, const DeviceBlock *ablock, const Kmer
     }
   ss->nhits = (int64_t) nhits;
 
+  TRACE("join: offsets");
   // pairsort key bytes, map.c:2917-2936
   int bytes[16], npass = 0;
   { int64_t powr; int nbyte;
@@ -383,11 +387,13 @@ SeedSet *merge_join(const KmerIndex *aidx, const DeviceBlock *ablock, const Kmer
   if (nhits >= (1ull << 30))
     fatal("Match_Filter: %llu seed hits exceed the 2^30 sort limit; lower -M or use -t",
           (unsigned long long) nhits);
+  TRACE("join: emit");
   SeedPair *rez = (SeedPair *) radix_sort16(h1, h2, (uint32_t) nhits, bytes, npass, hist, stream);
   LAUNCH(k_seed_sentinel, 1, 1, 0, stream, rez, nhits);
   CUDA_CHECK(cudaStreamSynchronize(stream));
   dfree(rez == h1 ? h2 : h1);
   dfree(hist); dfree(off); dfree(runs);
+  TRACE("join: seed sort");
   ss->hits = rez;
   return ss;
 }
