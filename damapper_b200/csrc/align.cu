@@ -44,30 +44,51 @@ struct WaveStats { unsigned long long nwaves, ncells, nalign, empty; };
 template <int DIR> __device__ __forceinline__ bool LT(int a, int b) { return DIR > 0 ? a < b : a > b; }
 template <int DIR> __device__ __forceinline__ bool GE(int a, int b) { return DIR > 0 ? a >= b : a <= b; }
 
+// Four consecutive bases starting at byte address p, in memory order (little endian): two aligned
+// word loads and a funnel shift (the block images carry >= 16 bytes of slack at both ends).
+__device__ __forceinline__ uint32_t load4(const uint8_t *p)
+{ const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t) 3);
+  return __funnelshift_r(w[0], w[1], (unsigned) (a & 3) * 8);
+}
+
 // Slide along diagonal k from b-coordinate y while bases match (align.c:748-768 / 1403-1423).
-// Returns the new y; hit: 1 = ran into the end of B, 2 = into the end of A.
+// Returns the new y; hit: 1 = ran into the end of B, 2 = into the end of A.  Four bases per
+// step: the first differing byte (xor) and the first terminator of B (bit 2 is set only in the
+// value 4) decide where and why the slide stops, exactly as the byte loop of the reference
+// (B's terminator is tested first, then the mismatch, then A's terminator).
 template <int DIR>
 __device__ __forceinline__ int slide(const uint8_t *__restrict__ aseq, const uint8_t *__restrict__ bseq,
                                      int k, int y, int &hit)
-{ const int off = (DIR > 0) ? 0 : -1;       // reverse_wave reads through aseq-1 / bseq-1 (:1017-1018)
-  const uint8_t *a = aseq + k + off, *b = bseq + off;
-  hit = 0;
+{ hit = 0;
   while (true)
-    { const int c = b[y];
-      if (c == 4) { hit = 1; break; }
-      const int d = a[y];
-      if (c != d)
-        { if (d == 4) hit = 2;
-          break;
+    { uint32_t wa, wb;
+      if (DIR > 0)
+        { wa = load4(aseq + k + y); wb = load4(bseq + y); }
+      else                                  // bytes y-1, y-2, .. of aseq-1+k / bseq-1 (:1017-1018)
+        { wa = __byte_perm(load4(aseq + k + y - 4), 0, 0x0123);
+          wb = __byte_perm(load4(bseq + y - 4), 0, 0x0123);
         }
-      y += DIR;
+      const uint32_t x = wa ^ wb, e = wb & 0x04040404u;
+      if ((x | e) == 0)
+        { y += 4 * DIR;
+          continue;
+        }
+      const int ix = x ? (__ffs(x) - 1) >> 3 : 4;      // first mismatch
+      const int ie = e ? (__ffs(e) - 1) >> 3 : 4;      // first terminator of B
+      if (ie <= ix)
+        { hit = 1;
+          return y + DIR * ie;
+        }
+      if (((wa >> (8 * ix)) & 0xff) == 4)
+        hit = 2;
+      return y + DIR * ix;
     }
-  return y;
 }
 
 // One forward (DIR=+1) or reverse (DIR=-1) extension from anti-diagonal mida on diagonal k0.
 // All lanes return the same value; path fields are warp-uniform.
-template <int DIR>
+template <int DIR, bool DOB>
 __device__ int wave(const WaveMem &wm, const AlignSpecD &sp, const uint8_t *__restrict__ aseq,
                     const uint8_t *__restrict__ bseq, PathD &apath, PathD &bpath, int k0, int mida,
                     int aoff, int boff, int *start_diag, WaveStats &st)
@@ -208,10 +229,13 @@ __device__ int wave(const WaveMem &wm, const AlignSpecD &sp, const uint8_t *__re
       const int  lup = (lane + 1) & 31, ldn = (lane + 31) & 31;
 
       // new outer diagonals inherit NA/NB from their inner neighbour (align.c:678-690)
-      { const int nau = __shfl_sync(0xffffffffu, rNA, lup), nbu = __shfl_sync(0xffffffffu, rNB, lup);
-        const int nad = __shfl_sync(0xffffffffu, rNA, ldn), nbd = __shfl_sync(0xffffffffu, rNB, ldn);
-        if (act && k == low) { rNA = nau; rNB = nbu; }
-        if (act && k == hgh) { rNA = nad; rNB = nbd; }
+      { const int inner = (k == low) ? lup : ldn;
+        const int nai = __shfl_sync(0xffffffffu, rNA, inner);
+        if (act && (k == low || k == hgh)) rNA = nai;
+        if (DOB)
+          { const int nbi = __shfl_sync(0xffffffffu, rNB, inner);
+            if (act && (k == low || k == hgh)) rNB = nbi;
+          }
       }
       const int vold = (act && k > low && k < hgh) ? rV : SENT;
       const int lp = (DIR > 0) ? lup : ldn, ln = (DIR > 0) ? ldn : lup;   // lanes of k+DIR, k-DIR
@@ -232,7 +256,8 @@ __device__ int wave(const WaveMem &wm, const AlignSpecD &sp, const uint8_t *__re
         }
       int m  = __shfl_sync(0xffffffffu, rM, srcl);
       int ha = __shfl_sync(0xffffffffu, rHA, srcl);
-      int hb = __shfl_sync(0xffffffffu, rHB, srcl);
+      int hb = 0;
+      if (DOB) hb = __shfl_sync(0xffffffffu, rHB, srcl);
       uint64_t b;
       { const unsigned tl = __shfl_sync(0xffffffffu, (unsigned) rT, srcl);
         const unsigned th = __shfl_sync(0xffffffffu, (unsigned) (rT >> 32), srcl);
@@ -253,16 +278,22 @@ __device__ int wave(const WaveMem &wm, const AlignSpecD &sp, const uint8_t *__re
             }
           c = (y << 1) + k;
           if (GE<DIR>(y + k, rNA))                      // align.c:771-793 / 1426-1448
-            { cntA = (DIR * (y + k - rNA)) / TS + 1;
+            { const int over = DIR * (y + k - rNA);
+              cntA = (over < TS) ? 1 : over / TS + 1;
               const int d0 = DIR * (cells[ha].mark - rNA);
               if (d0 >= 0)
-                skipA = (d0 / TS + 1 < cntA) ? d0 / TS + 1 : cntA;
+                { skipA = (d0 < TS) ? 1 : d0 / TS + 1;
+                  if (skipA > cntA) skipA = cntA;
+                }
             }
-          if (GE<DIR>(y, rNB))                          // align.c:795-817 / 1449-1471
-            { cntB = (DIR * (y - rNB)) / TS + 1;
+          if (DOB && GE<DIR>(y, rNB))                   // align.c:795-817 / 1449-1471
+            { const int over = DIR * (y - rNB);
+              cntB = (over < TS) ? 1 : over / TS + 1;
               const int d0 = DIR * (cells[hb].mark - rNB);
               if (d0 >= 0)
-                skipB = (d0 / TS + 1 < cntB) ? d0 / TS + 1 : cntB;
+                { skipB = (d0 < TS) ? 1 : d0 / TS + 1;
+                  if (skipB > cntB) skipB = cntB;
+                }
             }
         }
       else
@@ -290,8 +321,9 @@ __device__ int wave(const WaveMem &wm, const AlignSpecD &sp, const uint8_t *__re
           __syncwarp();
         }
       if (act)
-        { rNA += DIR * TS * cntA; rNB += DIR * TS * cntB;
-          rV = c; rT = b; rM = m; rHA = ha; rHB = hb;
+        { rNA += DIR * TS * cntA;
+          if (DOB) { rNB += DIR * TS * cntB; rHB = hb; }
+          rV = c; rT = b; rM = m; rHA = ha;
         }
 
 #define ROT(x)      __funnelshift_r((x), (x), base & 31)           /* bit i <-> diagonal base+i */
@@ -300,17 +332,21 @@ __device__ int wave(const WaveMem &wm, const AlignSpecD &sp, const uint8_t *__re
       // record breakers in scan order (align.c:819-833 / 1473-1487): prefix maximum along the
       // scan direction over the circular lane layout
       { const int cv = act ? ((DIR > 0) ? c : -c) : -IMAX;
-        int pm = cv;
-        for (int o = 1; o < width; o <<= 1)
-          { const int t = __shfl_sync(0xffffffffu, pm, (lane + DIR * o) & 31);
-            const bool ok = (DIR > 0) ? (k + o <= hgh) : (k - o >= low);
-            if (act && ok && t > pm) pm = t;
+        const int bv = (DIR > 0) ? besta : -besta;
+        // only points beyond besta can break the record; with a single one no scan is needed
+        const unsigned cand = __ballot_sync(0xffffffffu, cv > bv);
+        bool brk = (cv > bv);
+        if (cand & (cand - 1))
+          { int pm = cv;
+            for (int o = 1; o < width; o <<= 1)
+              { const int t = __shfl_sync(0xffffffffu, pm, (lane + DIR * o) & 31);
+                const bool ok = (DIR > 0) ? (k + o <= hgh) : (k - o >= low);
+                if (act && ok && t > pm) pm = t;
+              }
+            const int  before = __shfl_sync(0xffffffffu, pm, lp);
+            const bool hasprev = (DIR > 0) ? (k + 1 <= hgh) : (k - 1 >= low);
+            brk = brk && (!hasprev || cv > before);
           }
-        int before = __shfl_sync(0xffffffffu, pm, lp);
-        const int  bv = (DIR > 0) ? besta : -besta;
-        const bool hasprev = (DIR > 0) ? (k + 1 <= hgh) : (k - 1 >= low);
-        if (!hasprev || before < bv) before = bv;
-        const bool brk = act && (cv > before);
         const unsigned bm = __ballot_sync(0xffffffffu, brk);
         if (bm)
           { const bool good = brk && (m >= PATH_AVE);
@@ -333,7 +369,7 @@ __device__ int wave(const WaveMem &wm, const AlignSpecD &sp, const uint8_t *__re
                 trima  = __shfl_sync(0xffffffffu, c, lt);
                 trimy  = __shfl_sync(0xffffffffu, y, lt);
                 trimha = __shfl_sync(0xffffffffu, ha, lt);
-                trimhb = __shfl_sync(0xffffffffu, hb, lt);
+                if (DOB) trimhb = __shfl_sync(0xffffffffu, hb, lt);
                 trimd  = dif;
               }
           }
@@ -623,6 +659,8 @@ __device__ int wave(const WaveMem &wm, const AlignSpecD &sp, const uint8_t *__re
             }
         }
 
+      if (DOB)
+        {
       // B chain
       a = -1;
       for (h = trimhb; h >= 0; h = bq)
@@ -689,6 +727,7 @@ __device__ int wave(const WaveMem &wm, const AlignSpecD &sp, const uint8_t *__re
                 }
             }
         }
+        }
       r_x = trimx; r_y = trimy; r_d = trimd; r_at = atlen; r_bt = btlen;
     }
   err   = __shfl_sync(0xffffffffu, err, 0);
@@ -712,7 +751,9 @@ __device__ int wave(const WaveMem &wm, const AlignSpecD &sp, const uint8_t *__re
 #undef IX
 }
 
-// Local_Alignment as damapper calls it: (dg,dg,ad,-1,-1), reach = 1 (align.c:1727-1946)
+// Local_Alignment as damapper calls it: (dg,dg,ad,-1,-1), reach = 1 (align.c:1727-1946).
+// DOB = false skips the B-side Pebble chain: the B path is only consumed with -C (map.c:2556-2572).
+template <bool DOB>
 __device__ int local_alignment(const WaveMem &wm, const AlignSpecD &sp, const uint8_t *aseq, int alen,
                                const uint8_t *bseq, int blen, int acomp, int dg, int anti,
                                PathD &apath, PathD &bpath, WaveStats &st)
@@ -730,10 +771,10 @@ __device__ int local_alignment(const WaveMem &wm, const AlignSpecD &sp, const ui
     aoff = alen % sp.spacing;                            // align.c:1794-1797
   st.nalign += 1;
 
-  if ((err = wave<1>(wm, sp, aseq, bseq, apath, bpath, dg, anti, aoff, boff, &low, st)) != 0)
+  if ((err = wave<1, DOB>(wm, sp, aseq, bseq, apath, bpath, dg, anti, aoff, boff, &low, st)) != 0)
     return err;
   const bool fshort = ((apath.aepos + apath.bepos) - anti < DUB_TRIM);
-  if ((err = wave<-1>(wm, sp, aseq, bseq, apath, bpath, low, anti, aoff, boff, &low, st)) != 0)
+  if ((err = wave<-1, DOB>(wm, sp, aseq, bseq, apath, bpath, low, anti, aoff, boff, &low, st)) != 0)
     return err;
   const bool rshort = (anti - (apath.abpos + apath.bbpos) < DUB_TRIM);
 
@@ -748,7 +789,7 @@ __device__ int local_alignment(const WaveMem &wm, const AlignSpecD &sp, const ui
         { low = apath.abpos - apath.bbpos;
           anti = apath.abpos + apath.bbpos;
           apath.tlen = bpath.tlen = 0;
-          if ((err = wave<1>(wm, sp, aseq, bseq, apath, bpath, low, anti, aoff, boff, &low, st)) != 0)
+          if ((err = wave<1, DOB>(wm, sp, aseq, bseq, apath, bpath, low, anti, aoff, boff, &low, st)) != 0)
             return err;
         }
     }
@@ -757,7 +798,7 @@ __device__ int local_alignment(const WaveMem &wm, const AlignSpecD &sp, const ui
       anti = apath.aepos + apath.bepos;
       apath.tlen = bpath.tlen = 0;
       apath.diffs = 0;
-      if ((err = wave<-1>(wm, sp, aseq, bseq, apath, bpath, low, anti, aoff, boff, &low, st)) != 0)
+      if ((err = wave<-1, DOB>(wm, sp, aseq, bseq, apath, bpath, low, anti, aoff, boff, &low, st)) != 0)
         return err;
     }
 
@@ -785,7 +826,7 @@ __device__ int local_alignment(const WaveMem &wm, const AlignSpecD &sp, const ui
 
 // ---- job kernel: one warp per candidate (map.c:2460-2579) ----------------------------------
 
-template <bool BIG>
+template <bool BIG, bool DOB>
 __global__ void __launch_bounds__(ALIGN_WARPS * 32)
 k_align(AlignArgs A)
 { extern __shared__ __align__(16) unsigned char smem[];
@@ -837,7 +878,7 @@ k_align(AlignArgs A)
           if (cm) { const int ac = alen - apos, bc = blen - bpos; dg = ac - bc; ad = ac + bc; }
           else    { dg = apos - bpos; ad = apos + bpos; }
           PathD ap, bp;
-          const int err = local_alignment(wm, A.spec, aseq, alen, bseq, blen, cm, dg, ad, ap, bp, st);
+          const int err = local_alignment<DOB>(wm, A.spec, aseq, alen, bseq, blen, cm, dg, ad, ap, bp, st);
           if (err)
             { status = err;
               break;
@@ -893,21 +934,16 @@ k_align(AlignArgs A)
     }
 }
 
-template __global__ void k_align<false>(AlignArgs);
-template __global__ void k_align<true>(AlignArgs);
-
 void launch_align(const AlignArgs &A, bool big, int nblocks, cudaStream_t stream)
-{ if (big)
-    LAUNCH(k_align<true>, nblocks, ALIGN_WARPS * 32, 0, stream, A);
+{ const bool dob = (A.do_b != 0);
+  if (big)
+    { if (dob) LAUNCH((k_align<true, true>), nblocks, ALIGN_WARPS * 32, 0, stream, A);
+      else     LAUNCH((k_align<true, false>), nblocks, ALIGN_WARPS * 32, 0, stream, A);
+    }
   else
     { const size_t smem = (size_t) ALIGN_WARPS * ALIGN_STATE_BYTES(ALIGN_W);
-      static bool attr = false;
-      if (!attr)
-        { CUDA_CHECK(cudaFuncSetAttribute(k_align<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int) smem));
-          attr = true;
-        }
-      LAUNCH(k_align<false>, nblocks, ALIGN_WARPS * 32, smem, stream, A);
+      if (dob) LAUNCH((k_align<false, true>), nblocks, ALIGN_WARPS * 32, smem, stream, A);
+      else     LAUNCH((k_align<false, false>), nblocks, ALIGN_WARPS * 32, smem, stream, A);
     }
 }
 
