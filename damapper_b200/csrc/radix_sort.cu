@@ -1,6 +1,7 @@
 // Stable LSD radix sort of 16-byte records, 8-bit digits, single pass per digit
 // ("onesweep": per-tile digit counts are chained through a decoupled look-back so every
-// pass reads the array once and writes it once = 32 B per record per pass).
+// pass reads the array once and writes it once = 32 B per record per pass; the sorted tile
+// leaves shared memory through TMA bulk stores, one per digit run).
 //
 // Replaces lex_sort/lex_thread of the reference (map.c:181-444).  The reference sorts the
 // key bytes flagged in bytes[16], least significant first, with a stable scatter; any
@@ -9,10 +10,12 @@
 
 namespace damgpu {
 
-constexpr int RS_THREADS = 256;
-constexpr int RS_ITEMS   = 8;
-constexpr int RS_TILE    = RS_THREADS * RS_ITEMS;      // records per tile
+constexpr int RS_THREADS = 384;
+constexpr int RS_ITEMS   = 12;
+constexpr int RS_TILE    = RS_THREADS * RS_ITEMS;      // records per tile (4608 = 72 KB staged)
 constexpr int RS_WARPS   = RS_THREADS / 32;
+constexpr int RS_PROBE   = 4;                          // predecessors fetched per look-back round
+constexpr int RS_SMEM    = RS_TILE * 16;               // dynamic shared memory per CTA
 
 // look-back word: [31:30] flag, [29:0] value
 constexpr uint32_t FLAG_AGG = 1u << 30;
@@ -32,6 +35,19 @@ __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t *p)
 
 __device__ __forceinline__ void st_relaxed(uint32_t *p, uint32_t v)
 { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+
+// lanes of the warp holding the same 8-bit digit: eight ballots (MATCH.ANY costs ~2.6x as much on
+// sm_100 when most of the 32 digits are distinct, measured: tools/sortlab.cu)
+__device__ __forceinline__ uint32_t match_digit(uint32_t dig)
+{ uint32_t m = 0xffffffffu;
+#pragma unroll
+  for (int b = 0; b < 8; b++)
+    { const bool     p = (dig >> b) & 1;
+      const uint32_t v = __ballot_sync(0xffffffffu, p);
+      m &= p ? v : ~v;
+    }
+  return m;
+}
 
 // ---- histogram of every pass byte in one read ---------------------------------------
 
@@ -74,123 +90,147 @@ __global__ void __launch_bounds__(256) k_radix_prefix(uint32_t *hist)
 
 // ---- one scatter pass -----------------------------------------------------------------
 //
-// Tile = 2048 records, warp-striped: warp w owns records [w*256, w*256+256) of the tile, item
-// i of lane l is record i*32+l of that chunk.  Ranking is a warp-level multisplit
-// (__match_any_sync) on per-warp shared-memory counters, which keeps the order of equal
-// digits (stability).  Thread d (0..255) owns digit d for the cross-warp scan, the look-back
-// and the publication of the tile's counts.  Records are then staged in shared memory in
-// sorted order so the global writes are coalesced runs per digit.
+// Tile = 4608 records (384 threads x 12), warp-striped: warp w owns records [w*384, w*384+384)
+// of the tile, item i of lane l is record i*32+l of that chunk, so tile order = (warp, item,
+// lane).  Tile ids come from an atomic ticket, so a tile's predecessors are always held by CTAs
+// that started earlier and the look-back cannot deadlock.
+//   1. early counts: per-warp digit histograms with plain shared atomics; thread d sums digit d
+//      over the warps and publishes the tile aggregate at once, long before it is needed by
+//      successors;
+//   2. the per-warp counters are rewritten as staged start positions (exclusive over digits,
+//      then over warps);
+//   3. stable ranking: the lanes holding the same digit are found with ballots, the lowest of
+//      them bumps the warp's counter with one shared atomic and broadcasts the old value (the
+//      twelve items are issued in order and shared atomics of a warp execute in program order,
+//      which keeps equal digits in input order);
+//   4. records are staged in shared memory in sorted order (the counters die here);
+//   5. decoupled look-back for digit d, RS_PROBE predecessors per round trip;
+//   6. thread d hands the run of digit d to the TMA engine (cp.async.bulk shared -> global:
+//      16-byte records make every run a legal bulk copy), no per-record store instructions.
 
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, 2)
 k_radix_pass(const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t n, int byte,
              const uint32_t *__restrict__ gbase, uint32_t *tile_state, uint32_t *tile_counter)
-{ __shared__ uint4    stage[RS_TILE];                 // 32 KB; first 8 KB alias the counters
-  __shared__ uint32_t s_dbase[256];                   // first local rank of digit d in the tile
-  __shared__ uint32_t s_delta[256];                   // global index - local rank for digit d
+{ extern __shared__ uint4 stage[];                    // 72 KB; the first 12 KB alias the counters
   __shared__ uint32_t s_wsum[RS_WARPS];
   __shared__ uint32_t s_tile;
-  uint32_t (*whist)[256] = reinterpret_cast<uint32_t (*)[256]>(stage);   // [RS_WARPS][256]
+  uint32_t *whist = reinterpret_cast<uint32_t *>(stage);                 // [RS_WARPS][256]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lt = (1u << lane) - 1;
 
   if (tid == 0)
     s_tile = atomicAdd(tile_counter, 1u);
+  uint32_t *wh = whist + warp * 256;
+#pragma unroll
   for (int i = lane; i < 256; i += 32)
-    whist[warp][i] = 0;
+    wh[i] = 0;
   __syncthreads();
-  const uint32_t tile = s_tile;
-  const uint32_t base = tile * (uint32_t) RS_TILE + warp * (32 * RS_ITEMS) + lane;
-  const uint32_t nvalid = (n - tile * (uint32_t) RS_TILE < (uint32_t) RS_TILE)
-                              ? n - tile * (uint32_t) RS_TILE : (uint32_t) RS_TILE;
+  const uint32_t tile   = s_tile;
+  const uint32_t tbase  = tile * (uint32_t) RS_TILE;
+  const uint32_t nvalid = (n - tbase < (uint32_t) RS_TILE) ? n - tbase : (uint32_t) RS_TILE;
+  const uint32_t base   = tbase + warp * (32 * RS_ITEMS) + lane;
 
-  uint4    rec[RS_ITEMS];
-  uint32_t dig[RS_ITEMS], rank[RS_ITEMS];
+  uint4 rec[RS_ITEMS];
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; i++)                  // padding = all ones: digit 255, ranks after
+    { const uint32_t idx = base + i * 32;             // every real 255 of the (last) tile
+      rec[i] = (idx < n) ? __ldcs(in + idx)
+                         : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    }
 #pragma unroll
   for (int i = 0; i < RS_ITEMS; i++)
-    { uint32_t idx = base + i * 32;
-      if (idx < n)
-        { rec[i] = __ldcs(in + idx);
-          dig[i] = rec_byte(rec[i], byte);
-        }
-      else
-        { rec[i] = make_uint4(0, 0, 0, 0);
-          dig[i] = 255;                               // padding ranks after every real 255
-        }
-    }
-
-  const uint32_t lt = (1u << lane) - 1;
-#pragma unroll
-  for (int i = 0; i < RS_ITEMS; i++)
-    { uint32_t peers = __match_any_sync(0xffffffffu, dig[i]);
-      uint32_t prev  = whist[warp][dig[i]];
-      __syncwarp();
-      if ((peers & lt) == 0)
-        whist[warp][dig[i]] = prev + __popc(peers);
-      __syncwarp();
-      rank[i] = prev + __popc(peers & lt);
-    }
+    atomicAdd(&wh[rec_byte(rec[i], byte)], 1u);
   __syncthreads();
 
-  // digit d: exclusive scan over warps, tile count, look-back
-  { const int d = tid;
-    uint32_t run = 0;
+  // digit d = tid (threads 256.. only take part in the barriers)
+  uint32_t cnt = 0, dbase;
+  uint32_t *st = tile_state + (size_t) tile * 256 + (tid & 255);
+  if (tid < 256)
+    {
 #pragma unroll
-    for (int w = 0; w < RS_WARPS; w++)
-      { uint32_t c = whist[w][d];
-        whist[w][d] = run;
-        run += c;
-      }
-    if (d == 255)
-      run -= (uint32_t) RS_TILE - nvalid;             // padding is not counted
-    uint32_t *st = tile_state + (size_t) tile * 256 + d;
-    st_relaxed(st, (tile == 0 ? FLAG_INC : FLAG_AGG) | run);
-
-    // exclusive scan of the tile counts over digits -> s_dbase
-    uint32_t x = run;
+      for (int w = 0; w < RS_WARPS; w++)
+        cnt += whist[w * 256 + tid];
+      if (tid == 255)
+        cnt -= (uint32_t) RS_TILE - nvalid;           // padding is not counted
+      st_relaxed(st, (tile == 0 ? FLAG_INC : FLAG_AGG) | cnt);
+    }
+  { uint32_t x = cnt;                                 // exclusive scan over digits
+#pragma unroll
     for (int o = 1; o < 32; o <<= 1)
-      { uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
         if (lane >= o) x += y;
       }
     if (lane == 31) s_wsum[warp] = x;
     __syncthreads();
     uint32_t add = 0;
-    for (int w = 0; w < warp; w++) add += s_wsum[w];
-    const uint32_t dbase = x + add - run;
-
-    uint32_t excl = 0;
-    if (tile > 0)
-      { const uint32_t *p = st - 256;
-        while (true)
-          { uint32_t v = ld_relaxed(p);
-            if (v & FLAG_INC) { excl += v & VAL_MASK; break; }
-            if (v & FLAG_AGG) { excl += v & VAL_MASK; p -= 256; continue; }
-            __nanosleep(20);
-          }
-        st_relaxed(st, FLAG_INC | (excl + run));
-      }
-    s_dbase[d] = dbase;
-    s_delta[d] = gbase[d] + excl - dbase;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; w++)
+      if (w < warp) add += s_wsum[w];
+    dbase = x + add - cnt;
   }
+  if (tid < 256)
+    { uint32_t run = dbase;
+#pragma unroll
+      for (int w = 0; w < RS_WARPS; w++)
+        { const uint32_t c = whist[w * 256 + tid];
+          whist[w * 256 + tid] = run;
+          run += c;
+        }
+    }
   __syncthreads();
 
   uint32_t pos[RS_ITEMS];
 #pragma unroll
   for (int i = 0; i < RS_ITEMS; i++)
-    pos[i] = s_dbase[dig[i]] + whist[warp][dig[i]] + rank[i];
+    { const uint32_t dig   = rec_byte(rec[i], byte);
+      const uint32_t peers = match_digit(dig);
+      uint32_t old = 0;
+      if ((peers & lt) == 0)
+        old = atomicAdd(&wh[dig], (uint32_t) __popc(peers));
+      pos[i] = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1) + __popc(peers & lt);
+    }
   __syncthreads();                                    // counters die, staging area is live
 #pragma unroll
   for (int i = 0; i < RS_ITEMS; i++)
     stage[pos[i]] = rec[i];
-  __syncthreads();
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged data -> async proxy
 
+  uint32_t gdst = 0;
+  if (tid < 256)
+    { uint32_t excl = 0;
+      if (tile > 0)
+        { const uint32_t *col = tile_state + tid;
+          int64_t t = (int64_t) tile - 1;
+          bool done = false;
+          while (!done)
+            { uint32_t v[RS_PROBE];
 #pragma unroll
-  for (int i = 0; i < RS_ITEMS; i++)
-    { uint32_t j = tid + i * RS_THREADS;
-      if (j < nvalid)
-        { uint4 r = stage[j];
-          __stcs(out + (j + s_delta[rec_byte(r, byte)]), r);
+              for (int k = 0; k < RS_PROBE; k++)
+                v[k] = (t - k >= 0) ? ld_relaxed(col + (size_t) (t - k) * 256) : FLAG_INC;
+              int used = RS_PROBE;
+#pragma unroll
+              for (int k = 0; k < RS_PROBE; k++)
+                if (!done && used == RS_PROBE)
+                  { if (v[k] & FLAG_INC)      { excl += v[k] & VAL_MASK; done = true; }
+                    else if (v[k] & FLAG_AGG) excl += v[k] & VAL_MASK;
+                    else                      used = k;          // not published yet: ask again
+                  }
+              t -= used;
+            }
+          st_relaxed(st, FLAG_INC | (excl + cnt));
         }
+      gdst = gbase[tid] + excl;
     }
+  __syncthreads();                                    // staging complete
+
+  if (tid < 256 && cnt > 0)
+    { const uint32_t src = (uint32_t) __cvta_generic_to_shared(stage + dbase);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                   :: "l"(out + gdst), "r"(src), "r"(cnt * 16u) : "memory");
+    }
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory may be released
 }
 
 void radix_histogram(const void *recs, uint32_t n, const int *bytes, int npass, uint32_t *hist,
@@ -215,11 +255,16 @@ void *radix_sort16(void *a, void *b, uint32_t n, const int *bytes, int npass, ui
   uint32_t *state = dalloc<uint32_t>((size_t) ntiles * 256 + 1);
   uint32_t *counter = state + (size_t) ntiles * 256;
 
+  static bool attr_set = false;
+  if (!attr_set)
+    { CUDA_CHECK(cudaFuncSetAttribute(k_radix_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM));
+      attr_set = true;
+    }
   LAUNCH(k_radix_prefix, npass, 256, 0, stream, hist);
   uint4 *src = (uint4 *) a, *dst = (uint4 *) b;
   for (int p = 0; p < npass; p++)
     { CUDA_CHECK(cudaMemsetAsync(state, 0, sizeof(uint32_t) * ((size_t) ntiles * 256 + 1), stream));
-      LAUNCH(k_radix_pass, ntiles, RS_THREADS, 0, stream, src, dst, n, bytes[p],
+      LAUNCH(k_radix_pass, ntiles, RS_THREADS, RS_SMEM, stream, src, dst, n, bytes[p],
              hist + p * 256, state, counter);
       uint4 *t = src; src = dst; dst = t;
     }
