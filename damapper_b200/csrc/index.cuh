@@ -25,6 +25,8 @@ struct KmerIndex
   float    ms_extract = 0.f, ms_sort = 0.f;
   int      npass = 0;
   DeviceBlock *block = nullptr;   // block the list was built from, owned when set (layer 1)
+  mutable uint32_t *lut = nullptr;   // prefix table over the code, built by the first merge-join that
+                                  // searches this list (seed_join.cu), released with the index
 };
 
 DeviceBlock *upload_block(const uint8_t *bases, const int64_t *boff, const int32_t *rlen,
@@ -33,6 +35,8 @@ DeviceBlock *upload_block(const uint8_t *bases, const int64_t *boff, const int32
 void         free_block(DeviceBlock *blk);
 // complement_DB(block, inplace) of the reference driver (damapper.c:433-469), on the device
 void         complement_block(DeviceBlock *blk, cudaStream_t stream);
+// reverse-complemented copy of every read into dst_bases (same layout as blk->bases)
+void         revcomp_copy_block(const DeviceBlock *blk, uint8_t *dst_bases, cudaStream_t stream);
 KmerIndex   *sort_kmers(const DeviceBlock *blk, int K, int suppress, cudaStream_t stream);
 void         free_index(KmerIndex *idx);
 

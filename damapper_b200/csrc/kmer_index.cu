@@ -278,6 +278,47 @@ k_complement(uint8_t *bases, const int64_t *__restrict__ boff, int nreads, int64
     }
 }
 
+// Out-of-place reverse complement of every read, one warp per read (grid-stride): position i of
+// the copy is 3 - base[len-1-i]; the terminators (and the leading 4) are copied as they are.
+__global__ void __launch_bounds__(256)
+k_revcomp_copy(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+               const int64_t *__restrict__ boff, int nreads)
+{ const int lane = threadIdx.x & 31;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nreads; r += nw)
+    { const int64_t b0 = boff[r];
+      const int len = (int) (boff[r + 1] - b0 - 1);
+      const uint8_t *s = src + b0;
+      uint8_t *d = dst + b0;
+      if (lane == 0)
+        { d[len] = s[len];
+          if (r == 0) d[-1] = s[-1];
+        }
+      // head: bytes up to the first 4-byte aligned destination address
+      const int headn = (int) ((4 - ((uintptr_t) d & 3)) & 3);
+      const int h = headn < len ? headn : len;
+      if (lane < h)
+        d[lane] = (uint8_t) (3 - s[len - 1 - lane]);
+      const int nwords = (len - h) >> 2;
+      for (int w = lane; w < nwords; w += 32)
+        { const int i = h + 4 * w;                  // destination bytes i..i+3 <- source len-1-i .. len-4-i
+          const uint8_t *q = s + (len - 4 - i);
+          const uint32_t v = (uint32_t) q[0] | ((uint32_t) q[1] << 8) | ((uint32_t) q[2] << 16) | ((uint32_t) q[3] << 24);
+          *reinterpret_cast<uint32_t *>(d + i) = 0x03030303u - __byte_perm(v, 0, 0x0123);
+        }
+      const int done = h + 4 * nwords;
+      if (lane < len - done)
+        d[done + lane] = (uint8_t) (3 - s[len - 1 - (done + lane)]);
+    }
+}
+
+void revcomp_copy_block(const DeviceBlock *blk, uint8_t *dst_bases, cudaStream_t stream)
+{ if (blk->nreads == 0) return;
+  int grid = (blk->nreads + 7) / 8;
+  if (grid > sm_count() * 16) grid = sm_count() * 16;
+  LAUNCH(k_revcomp_copy, grid, 256, 0, stream, blk->bases, dst_bases, blk->boff, blk->nreads);
+}
+
 void complement_block(DeviceBlock *blk, cudaStream_t stream)
 { if (blk->nreads == 0) return;
   int64_t nb = (blk->total + 255) / 256;
@@ -372,6 +413,7 @@ KmerIndex *sort_kmers(const DeviceBlock *blk, int K, int suppress, cudaStream_t 
 void free_index(KmerIndex *idx)
 { if (idx == nullptr) return;
   dfree(idx->list);
+  dfree(idx->lut);
   free_block(idx->block);
   delete idx;
 }

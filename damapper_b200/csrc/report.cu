@@ -583,6 +583,44 @@ void build_align_spec(double ave_corr, const float freq[4], int *ave_path, int16
   set_table(0, 0, 0, 0, mscore, dscore, table, score);
 }
 
+// exclusive scan of used[0..n) into off[0..n] (single CTA; n = reads of the block)
+__global__ void __launch_bounds__(1024) k_scan_used(const int64_t *__restrict__ used, int n, int64_t *off)
+{ __shared__ int64_t part[1024];
+  const int t = threadIdx.x;
+  const int per = (n + 1023) / 1024;
+  const int lo = t * per, hi = (lo + per < n) ? lo + per : n;
+  int64_t s = 0;
+  for (int i = lo; i < hi; i++) s += used[i];
+  part[t] = s;
+  __syncthreads();
+  if (t == 0)
+    { int64_t run = 0;
+      for (int i = 0; i < 1024; i++)
+        { const int64_t c = part[i]; part[i] = run; run += c; }
+      off[n] = run;
+    }
+  __syncthreads();
+  int64_t run = part[t];
+  for (int i = lo; i < hi; i++)
+    { off[i] = run; run += used[i]; }
+}
+
+// per-read output slots (worst-case sized) -> dense stream in read order, one warp per read
+__global__ void __launch_bounds__(256)
+k_compact_out(const uint8_t *__restrict__ src, const int64_t *__restrict__ src_off,
+              const int64_t *__restrict__ used, const int64_t *__restrict__ dst_off, int n,
+              uint8_t *__restrict__ dst)
+{ const int lane = threadIdx.x & 31;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += nw)
+    { const uint8_t *s = src + src_off[r];
+      uint8_t *d = dst + dst_off[r];
+      const int64_t len = used[r];
+      for (int64_t i = lane; i < len; i += 32)
+        d[i] = s[i];
+    }
+}
+
 template <typename T> static std::vector<T> d2h(const T *d, size_t n)
 { std::vector<T> v(n);
   if (n) CUDA_CHECK(cudaMemcpy(v.data(), d, sizeof(T) * n, cudaMemcpyDeviceToHost));
@@ -614,9 +652,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   DeviceBlock rc = *rd;
   rc.raw = dalloc<uint8_t>((size_t) rd->total + 64);
   rc.bases = rc.raw + 16;
-  CUDA_CHECK(cudaMemcpyAsync(rc.bases - 1, rd->bases - 1, (size_t) rd->total + 1,
-                             cudaMemcpyDeviceToDevice, stream));
-  complement_block(&rc, stream);
+  revcomp_copy_block(rd, rc.bases, stream);
 
   TRACE("report: spec+rc copy");
   // jobs = live candidates in (read, list order)
@@ -780,30 +816,32 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
 
   TRACE("report: k_report");
   // copy out and compact per read (record order = read order, as the per-thread files concatenate)
-  { std::vector<uint8_t> ra = d2h(R.out_a, (size_t) ta);
-    std::vector<int64_t> ua = d2h(R.used_a, n);
-    std::vector<int> na = d2h(R.nrec_a, n);
-    out->read_off_a.resize(n + 1);
-    for (int i = 0; i < n; i++)
-      { out->read_off_a[i] = (int64_t) out->a.size();
-        out->a.insert(out->a.end(), ra.begin() + outa_off[i], ra.begin() + outa_off[i] + ua[i]);
-        out->nrec_a += na[i];
+  { int64_t *d_off = dalloc<int64_t>((size_t) n + 1);
+    const int cgrid = std::min((n + 7) / 8, sm_count() * 16);
+    for (int fam = 0; fam < (do_b ? 2 : 1); fam++)
+      { const uint8_t *src = fam ? R.out_b : R.out_a;
+        const int64_t *soff = fam ? d_outb_off : d_outa_off;
+        const int64_t *used = fam ? R.used_b : R.used_a;
+        std::vector<uint8_t> &dstv = fam ? out->b : out->a;
+        std::vector<int64_t> &roff = fam ? out->read_off_b : out->read_off_a;
+        std::vector<int>     &nrec = fam ? out->read_nrec_b : out->read_nrec_a;
+        LAUNCH(k_scan_used, 1, 1024, 0, stream, used, n, d_off);
+        roff = d2h(d_off, (size_t) n + 1);
+        const int64_t tot = roff[n];
+        uint8_t *dense = dalloc<uint8_t>((size_t) tot + 1);
+        if (n > 0 && tot > 0)
+          LAUNCH(k_compact_out, cgrid, 256, 0, stream, src, soff, used, d_off, n, dense);
+        dstv.resize((size_t) tot);
+        if (tot > 0)
+          CUDA_CHECK(cudaMemcpyAsync(dstv.data(), dense, (size_t) tot, cudaMemcpyDeviceToHost, stream));
+        nrec = d2h(fam ? R.nrec_b : R.nrec_a, (size_t) n);
+        int64_t total = 0;
+        for (int i = 0; i < n; i++) total += nrec[i];
+        if (fam) out->nrec_b = total; else out->nrec_a = total;
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        dfree(dense);
       }
-    out->read_off_a[n] = (int64_t) out->a.size();
-    out->read_nrec_a = na;
-    if (do_b)
-      { std::vector<uint8_t> rb = d2h(R.out_b, (size_t) tbb);
-        std::vector<int64_t> ub = d2h(R.used_b, n);
-        std::vector<int> nb = d2h(R.nrec_b, n);
-        out->read_off_b.resize(n + 1);
-        for (int i = 0; i < n; i++)
-          { out->read_off_b[i] = (int64_t) out->b.size();
-            out->b.insert(out->b.end(), rb.begin() + outb_off[i], rb.begin() + outb_off[i] + ub[i]);
-            out->nrec_b += nb[i];
-          }
-        out->read_off_b[n] = (int64_t) out->b.size();
-        out->read_nrec_b = nb;
-      }
+    dfree(d_off);
     if (g_par.profile)
       out->prof = d2h(R.prof, (size_t) m->h_coff[n]);
     out->h2_events = (int64_t) d2h(d_ull + 6, 1)[0];

@@ -55,7 +55,11 @@ __device__ __forceinline__ int run_end(const KmerPos *__restrict__ L, int s, int
   return hi;
 }
 
-// ---- match A run heads against B, ordered compaction of matching run pairs ----------------
+// ---- match driver run heads against the target list, ordered compaction of matching run pairs --
+// The kernel's "A" is the driver (the SHORTER of the two lists: one lookup per distinct driver
+// code), its "B" the target searched through the prefix table; with swap != 0 the driver is the
+// reference list and the emitted Run has the roles put back.  Both lists are code-sorted, so the
+// run list comes out in code order either way.
 constexpr int JM_THREADS = 256;
 constexpr int JM_ITEMS   = 4;
 constexpr int JM_TILE    = JM_THREADS * JM_ITEMS;
@@ -63,7 +67,7 @@ constexpr uint64_t J_AGG = 1ull << 62, J_INC = 2ull << 62, J_VAL = (1ull << 62) 
 
 __global__ void __launch_bounds__(JM_THREADS)
 k_join_match(const KmerPos *__restrict__ A, int alen, const KmerPos *__restrict__ B, int blen,
-             const uint32_t *__restrict__ lut, int shift, Run *__restrict__ runs,
+             const uint32_t *__restrict__ lut, int shift, int swap, Run *__restrict__ runs,
              uint64_t *tile_state, uint32_t *tile_counter, uint32_t *nruns_out)
 { __shared__ uint32_t s_tile, s_wsum[JM_THREADS / 32];
   __shared__ uint64_t s_excl;
@@ -98,7 +102,10 @@ k_join_match(const KmerPos *__restrict__ A, int alen, const KmerPos *__restrict_
       if (lo >= blen || B[lo].code != c) continue;
       const int e  = run_end(B, lo, blen, c);
       const int ae = run_end(A, (int) i, alen, c);
-      mine[nm].ia = (int) i; mine[nm].na = ae - (int) i; mine[nm].jb = lo; mine[nm].nb = e - lo;
+      if (swap)                                        // driver = reference list, target = reads list
+        { mine[nm].ia = lo; mine[nm].na = e - lo; mine[nm].jb = (int) i; mine[nm].nb = ae - (int) i; }
+      else
+        { mine[nm].ia = (int) i; mine[nm].na = ae - (int) i; mine[nm].jb = lo; mine[nm].nb = e - lo; }
       nm++;
     }
 
@@ -300,23 +307,35 @@ SeedSet *merge_join(const KmerIndex *aidx, const DeviceBlock *ablock, const Kmer
   const KmerPos *A = aidx->list, *B = bidx->list;
 
   TRACE(nullptr);
-  // prefix table: about 4 B records per bucket, at most 2^24 buckets
+  // driver = shorter list; target = longer list, searched through a prefix table over the top P
+  // bits of the code (about 4 target records per bucket).  The table of a reads index is kept
+  // with the index: it serves both orientations and every reference block.
+  const bool swap = (blen < alen);
+  const KmerPos *D = swap ? B : A, *T = swap ? A : B;
+  const int dlen = swap ? blen : alen, tlen = swap ? alen : blen;
   int P = 1;
-  while ((1ll << P) * 4 < blen && P < 24) P++;
+  while ((1ll << P) * 4 < tlen && P < 26) P++;
   if (P > 2 * K) P = 2 * K;
   const int shift = 2 * K - P;
   const uint32_t np = 1u << P;
-  uint32_t *lut = dalloc<uint32_t>((size_t) np + 2);
-  LAUNCH(k_build_lut, (blen + 256) / 256, 256, 0, stream, B, blen, shift, np, lut);
+  uint32_t *lut;
+  if (swap && aidx->lut != nullptr)
+    lut = aidx->lut;
+  else
+    { lut = dalloc<uint32_t>((size_t) np + 2);
+      LAUNCH(k_build_lut, (tlen + 256) / 256, 256, 0, stream, T, tlen, shift, np, lut);
+      if (swap)
+        aidx->lut = lut;
+    }
 
-  const uint32_t ntiles = (uint32_t) (((int64_t) alen + JM_TILE - 1) / JM_TILE);
+  const uint32_t ntiles = (uint32_t) (((int64_t) dlen + JM_TILE - 1) / JM_TILE);
   uint64_t *state = dalloc<uint64_t>((size_t) ntiles + 2);
   CUDA_CHECK(cudaMemsetAsync(state, 0, sizeof(uint64_t) * ((size_t) ntiles + 2), stream));
   uint32_t *counter = reinterpret_cast<uint32_t *>(state + ntiles);      // [0]=tile counter, [1]=nruns
-  // worst case every A record heads a matching run (normally a few percent do)
-  Run *runs = dalloc<Run>((size_t) alen + 1);
-  LAUNCH(k_join_match, ntiles, JM_THREADS, 0, stream, A, alen, B, blen, lut, shift, runs, state,
-         counter, counter + 1);
+  // worst case every driver record heads a matching run (normally a few percent do)
+  Run *runs = dalloc<Run>((size_t) dlen + 1);
+  LAUNCH(k_join_match, ntiles, JM_THREADS, 0, stream, D, dlen, T, tlen, lut, shift, swap ? 1 : 0,
+         runs, state, counter, counter + 1);
   uint32_t nruns = 0;
   CUDA_CHECK(cudaMemcpyAsync(&nruns, counter + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
 
@@ -324,7 +343,8 @@ SeedSet *merge_join(const KmerIndex *aidx, const DeviceBlock *ablock, const Kmer
   unsigned long long *gram = dalloc<unsigned long long>(MAXGRAM + 1);
   CUDA_CHECK(cudaMemsetAsync(gram, 0, sizeof(unsigned long long) * (MAXGRAM + 1), stream));
   CUDA_CHECK(cudaStreamSynchronize(stream));
-  dfree(lut); dfree(state);
+  if (!swap) dfree(lut);
+  dfree(state);
 
   if (nruns > 0)
     { int grid = (int) ((nruns + 255) / 256);

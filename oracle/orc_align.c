@@ -86,6 +86,29 @@ void orc_work_free(orc_work *w)
   free(w);
 }
 
+/* ORC_BANDSTATS=1: histogram of band widths per wave and of the per-call maxima (dev aid) */
+static long long g_bandhist[64], g_maxhist[64], g_cellhist[64];
+static int g_bandstats = -1, g_callmax = 0;
+static void band_note(int width)
+{ if (g_bandstats < 0) g_bandstats = (getenv("ORC_BANDSTATS") != NULL);
+  if (!g_bandstats) return;
+  g_bandhist[width < 63 ? width : 63] += 1;
+  if (width > g_callmax) g_callmax = width;
+}
+static void call_note(int avail)
+{ if (g_bandstats <= 0) return;
+  g_maxhist[g_callmax < 63 ? g_callmax : 63] += 1; g_callmax = 0;
+  { int b = avail / 64; g_cellhist[b < 63 ? b : 63] += 1; }
+}
+void orc_bandstats_print(void)
+{ int i;
+  if (g_bandstats <= 0) return;
+  fprintf(stderr,"band width per wave:"); for (i = 0; i < 64; i++) if (g_bandhist[i]) fprintf(stderr," %d:%lld",i,g_bandhist[i]);
+  fprintf(stderr,"\nmax band per call:"); for (i = 0; i < 64; i++) if (g_maxhist[i]) fprintf(stderr," %d:%lld",i,g_maxhist[i]);
+  fprintf(stderr,"\ncells per call (x64):"); for (i = 0; i < 64; i++) if (g_cellhist[i]) fprintf(stderr," %d:%lld",i,g_cellhist[i]);
+  fprintf(stderr,"\n");
+}
+
 static inline int new_cell(orc_work *w, int *avail, int ptr, int diag, int diff, int mark)
 { orc_pebble *pb;
   if (*avail >= w->cmax)
@@ -98,7 +121,8 @@ static inline int new_cell(orc_work *w, int *avail, int ptr, int diag, int diff,
 }
 
 static void band_check(int low, int hgh)
-{ if (hgh-low+4 >= WSIZE)
+{ band_note(hgh-low+1);
+  if (hgh-low+4 >= WSIZE)
     { fprintf(stderr,"oracle: wave band wider than %d diagonals\n",WSIZE); exit (1); }
 }
 
@@ -376,6 +400,7 @@ static void forward_wave(orc_work *work, const orc_aspec *spec, const uint8_t *a
       work->ncells += (hgh-low)+1;
     }
 
+  call_note(avail);
   cells = work->cells;
   { uint16_t *atrace = apath->trace;                         /* align.c:900-1007 */
     uint16_t *btrace = bpath->trace;
@@ -735,6 +760,7 @@ static void reverse_wave(orc_work *work, const orc_aspec *spec, const uint8_t *a
       work->ncells += (hgh-low)+1;
     }
 
+  call_note(avail);
   cells = work->cells;
   { uint16_t *atrace = apath->trace;                         /* align.c:1554-1717 */
     uint16_t *btrace = bpath->trace;

@@ -690,6 +690,7 @@ void orc_report(orc_mapper *m, const orc_block *ref,
 
   free(part); free(perm); free(linker); free(bmatch); free(amatch);
   free(tb.trace); free(acomp); free(tables);
+  { extern void orc_bandstats_print(void); orc_bandstats_print(); }
   orc_work_free(work);
 
   *abuf = m->abuf; *alen_out = m->alen; *anrec = m->anrec;
