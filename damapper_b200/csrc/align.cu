@@ -827,7 +827,7 @@ __device__ int local_alignment(const WaveMem &wm, const AlignSpecD &sp, const ui
 // ---- job kernel: one warp per candidate (map.c:2460-2579) ----------------------------------
 
 template <bool BIG, bool DOB>
-__global__ void __launch_bounds__(ALIGN_WARPS * 32)
+__global__ void __launch_bounds__(ALIGN_WARPS * 32, ALIGN_MINB)
 k_align(AlignArgs A)
 { extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;

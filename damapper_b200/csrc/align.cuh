@@ -6,9 +6,17 @@
 namespace damgpu {
 
 constexpr int ALIGN_WARPS = 4;            // warps (jobs in flight) per CTA
+#ifndef ALIGN_MINB
+#define ALIGN_MINB 5                      // resident CTAs per SM the register allocation aims at
+#endif
 constexpr int ALIGN_W     = 128;          // diagonal window in shared memory
 constexpr int ALIGN_W_BIG = 8192;         // diagonal window of the overflow kernel (global memory)
 #define ALIGN_STATE_BYTES(W) ((size_t) (W) * (2 * 8 + 10 * 4))
+constexpr int LANE_WARPS  = 4;            // lane kernel: warps per CTA, one CTA per SM
+constexpr int LANE_W      = 64;           // lane kernel: diagonal window per lane (shared memory)
+constexpr int LANE_WIN    = 32;           // lane kernel: words of each per-lane sequence window
+#define LANE_WARP_WORDS(dob) ((((dob) ? 6 : 5) * LANE_W + 2 * LANE_WIN + 20) * 32)
+#define LANE_ARENA(tps) (16 * (tps) + 512)   // Pebble cells per job, tps = read length / spacing
 
 // What the waves need of _Align_Spec (align.c:183-191); tables built on the host (align.c:207-269)
 struct AlignSpecD
@@ -26,6 +34,26 @@ struct AlnRec
   int       a[6];                         // abpos, bbpos, aepos, bepos, diffs, tlen
   int       b[6];
   long long atrace, btrace;               // offsets into the uint16 trace pool
+};
+
+constexpr int PACK_WARPS  = 4;            // packed kernel: warps per CTA
+constexpr int PACK_W      = 64;           // packed kernel: diagonal window per slot (shared memory)
+#define PACK_SLOT_WORDS(dob) (((dob) ? 10 : 9) * PACK_W + 8)       /* +8: slots start 8 banks apart */
+#define PACK_WARP_WORDS(g, dob) ((g) * 16 + (g) * PACK_SLOT_WORDS(dob))
+
+// Lane kernel (align_lane.cu): what k_unwind needs of one wave call, and the calls whose traces
+// make up one kept alignment (forward then reverse; a DUB_TRIM re-run stands alone).
+struct LaneCall
+{ long long cells;                        // first Pebble of the call in the arena
+  int       dir, mida, aoff;              // direction, start anti-diagonal, A trace phase
+  int       ha, hb;                       // heads of the A and B Pebble chains
+  int       x, y, d;                      // end point (a, b) and differences
+  int       pad;
+};
+struct LaneUnwind
+{ int      ncalls;                        // -1: record was produced by the warp kernels
+  int      acomp, job, pad;
+  LaneCall call[2];
 };
 
 struct AlignArgs
@@ -51,8 +79,18 @@ struct AlignArgs
   uint16_t        *traces; unsigned long long *trace_top; long long trace_cap;
   int             *nfailed;
   unsigned long long *stats;              // nalign, nwaves, ncells, empty-band events
+  // lane kernel
+  void            *lane_cells;            // Pebble arena: per job 8*(rlen/spacing)+256 cells
+  const long long *lane_cell_base;        // per read: arena index of its first job
+  const int64_t   *lane_job_off;          // per read: index of its first job
+  LaneUnwind      *unwind;                // per alignment record (aln_cap)
+  uint16_t        *lane_tscratch;         // per alignment record: 4*tcap trace scratch
 };
 
 void launch_align(const AlignArgs &A, bool big, int nblocks, cudaStream_t stream);
+void launch_align_pack(const AlignArgs &A, int njobs, cudaStream_t stream);
+int  lane_warps(bool dob);
+void launch_align_lane(const AlignArgs &A, int nblocks, cudaStream_t stream);
+void launch_unwind(const AlignArgs &A, int max_alns, cudaStream_t stream);
 
 }  // namespace damgpu

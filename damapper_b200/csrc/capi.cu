@@ -26,6 +26,7 @@ static float       g_sort_times[3] = { 0, 0, 0 };
 
 Params g_par;          // filter parameters + the map.h globals
 bool   g_trace = false;
+int    g_align_tier = 0, g_align_slots = 4;
 
 void trace_mark(const char *name)
 { static double last = 0;
@@ -143,6 +144,10 @@ int damgpu_init(int device)
     }
   g_sms = prop.multiProcessorCount;
   g_trace = (getenv("DAMGPU_TRACE") != nullptr);
+  if (const char *t = getenv("DAMGPU_ALIGN"))
+    g_align_tier = !strcmp(t, "warp") ? 0 : !strcmp(t, "lane") ? 1 : 2;
+  if (const char *t = getenv("DAMGPU_SLOTS"))
+    g_align_slots = atoi(t);
   g_ready = true;
   return 0;
 }

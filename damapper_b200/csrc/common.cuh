@@ -54,6 +54,10 @@ int sm_count();
 void trace_mark(const char *name);
 #define TRACE(name) do { if (damgpu::g_trace) damgpu::trace_mark(name); } while (0)
 extern bool g_trace;
+// first tier of the alignment phase: 0 = warp per job (align.cu), 1 = thread per job
+// (align_lane.cu), 2 = several jobs per warp, diagonals packed onto the lanes (align_pack.cu).
+// DAMGPU_ALIGN=warp|lane|pack and DAMGPU_SLOTS=2|4|8 override (development).
+extern int g_align_tier, g_align_slots;
 
 // ---- radix_sort.cu -------------------------------------------------------------------
 // Stable LSD radix sort of n 16-byte records on the key bytes listed in `bytes` (least

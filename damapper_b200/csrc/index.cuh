@@ -5,11 +5,13 @@
 
 namespace damgpu {
 
+constexpr int BLOCK_SLACK = 256;   // readable bytes before bases[-1] and after the last terminator
+
 // Device image of a loaded DB block (Load_All_Reads, DB.c:1389-1441): bases[-1] == 4, read i at
 // bases[boff[i] .. boff[i]+rlen[i]) followed by a 4.
 struct DeviceBlock
 { uint8_t *raw = nullptr;       // allocation
-  uint8_t *bases = nullptr;     // raw+16, 16-byte aligned
+  uint8_t *bases = nullptr;     // raw+BLOCK_SLACK, 16-byte aligned
   int64_t *boff = nullptr;      // nreads+1
   int32_t *rlen = nullptr;
   int      nreads = 0, tfirst = 0, maxlen = 0;

@@ -238,9 +238,10 @@ DeviceBlock *upload_block(const uint8_t *bases, const int64_t *boff, const int32
   blk->nreads = nreads; blk->tfirst = tfirst; blk->maxlen = maxlen; blk->totlen = totlen;
   blk->sizeof_db = sizeof_db;
   blk->total = boff[nreads];
-  // image = leading 4 + bases; kept 16-byte aligned at bases[0] by 15 bytes of lead padding
-  blk->raw = dalloc<uint8_t>((size_t) blk->total + 64);
-  blk->bases = blk->raw + 16;
+  // image = leading 4 + bases; bases[0] is 16-byte aligned; BLOCK_SLACK bytes on both sides may be
+  // read (never interpreted) by the window prefetch of the alignment kernels
+  blk->raw = dalloc<uint8_t>((size_t) blk->total + 2 * BLOCK_SLACK);
+  blk->bases = blk->raw + BLOCK_SLACK;
   CUDA_CHECK(cudaMemcpyAsync(blk->bases - 1, bases - 1, (size_t) blk->total + 1,
                              cudaMemcpyHostToDevice, stream));
   blk->boff = dalloc<int64_t>(nreads + 1);

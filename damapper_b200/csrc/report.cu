@@ -650,8 +650,8 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
 
   // reverse-complemented copy of the reads (complement, map.c:1940-1948, once per block)
   DeviceBlock rc = *rd;
-  rc.raw = dalloc<uint8_t>((size_t) rd->total + 64);
-  rc.bases = rc.raw + 16;
+  rc.raw = dalloc<uint8_t>((size_t) rd->total + 2 * BLOCK_SLACK);
+  rc.bases = rc.raw + BLOCK_SLACK;
   revcomp_copy_block(rd, rc.bases, stream);
 
   TRACE("report: spec+rc copy");
@@ -691,6 +691,20 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   AlnRec   *d_alns = dalloc<AlnRec>((size_t) aln_cap);
   uint16_t *d_traces = dalloc<uint16_t>((size_t) trace_cap);
 
+  // lane kernel (first tier): per-job Pebble arenas, unwind records, trace scratch per record
+  std::vector<long long> cell_base(n + 1);
+  long long ncell = 0;
+  for (int i = 0; i < n; i++)
+    { cell_base[i] = ncell;
+      ncell += (long long) cnt[i] * LANE_ARENA(rd->h_rlen[i] / S);
+    }
+  cell_base[n] = ncell;
+  long long  *d_cell_base = h2d(cell_base);
+  void       *d_lane_cells = dalloc<unsigned char>((size_t) ncell * 16 + 16);
+  LaneUnwind *d_unwind = dalloc<LaneUnwind>((size_t) aln_cap);
+  uint16_t   *d_lane_tscr = dalloc<uint16_t>((size_t) aln_cap * 4 * tcap);
+  CUDA_CHECK(cudaMemsetAsync(d_unwind, 0xff, sizeof(LaneUnwind) * (size_t) aln_cap, stream));
+
   AlignArgs A;
   memset(&A, 0, sizeof(A));
   A.jobs = d_jobs; A.job_list = nullptr; A.njobs = njobs; A.job_counter = d_ctr;
@@ -704,13 +718,27 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   A.alns = d_alns; A.aln_top = d_ctr + 1; A.aln_cap = aln_cap;
   A.traces = d_traces; A.trace_top = d_ull; A.trace_cap = trace_cap;
   A.nfailed = d_ctr + 2; A.stats = d_ull + 1;
+  A.lane_cells = d_lane_cells; A.lane_cell_base = d_cell_base; A.lane_job_off = d_job_off;
+  A.unwind = d_unwind; A.lane_tscratch = d_lane_tscr;
 
   TRACE("report: alloc");
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_time_kernels)
     { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, stream); }
   if (njobs > 0)
-    launch_align(A, false, nblocks, stream);
+    { if (g_align_tier == 2)
+        { launch_align_pack(A, njobs, stream);
+          launch_unwind(A, aln_cap, stream);
+        }
+      else if (g_align_tier == 1)
+        { const int lpb = lane_warps(do_b != 0) * 32;
+          const int lblocks = std::min((njobs + lpb - 1) / lpb, sm_count());
+          launch_align_lane(A, lblocks, stream);
+          launch_unwind(A, aln_cap, stream);
+        }
+      else
+        launch_align(A, false, nblocks, stream);
+    }
   if (g_time_kernels)
     { cudaEventRecord(e1, stream); cudaEventSynchronize(e1);
       cudaEventElapsedTime(&out->ms_align, e0, e1);
@@ -755,12 +783,21 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
       CUDA_CHECK(cudaMemcpy(d_ctr, zero, sizeof(int), cudaMemcpyHostToDevice));       // job counter
       CUDA_CHECK(cudaMemcpy(d_ctr + 2, zero, sizeof(int), cudaMemcpyHostToDevice));   // nfailed
       A.job_list = d_list; A.njobs = nfailed; A.big_state = d_big;
-      launch_align(A, true, nbig / ALIGN_WARPS, stream);
+      if (g_align_tier != 0 && round == 0)                   // second tier: warp per job, window 128
+        launch_align(A, false, std::min((nfailed + ALIGN_WARPS - 1) / ALIGN_WARPS, nblocks), stream);
+      else
+        launch_align(A, true, nbig / ALIGN_WARPS, stream);
     }
 
   std::vector<unsigned long long> stats = d2h(d_ull, 8);
   out->nalign = (int64_t) stats[1]; out->nwaves = (int64_t) stats[2]; out->ncells = (int64_t) stats[3];
   out->empty_band = (int64_t) stats[4];
+  if (g_trace && stats[7] != 0)
+    fprintf(stderr, "[trace] longest job: %llu waves in %llu alignments; mean %.0f waves per job\n",
+            stats[7] >> 20, stats[7] & 0xfffff, njobs ? (double) stats[2] / njobs : 0.);
+  if (g_trace && stats[5] != 0)
+    fprintf(stderr, "[trace] lane kernel hand-offs: band %llu, cells %llu, trace %llu, other %llu\n",
+            stats[5] & 0xffff, (stats[5] >> 16) & 0xffff, (stats[5] >> 32) & 0xffff, stats[5] >> 48);
 
   TRACE("report: overflow loop");
   // per-read sizing of the second half
@@ -855,6 +892,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   dfree(d_novl); dfree(d_asum); dfree(d_bsum);
   dfree(d_alns); dfree(d_traces); dfree(d_list); dfree(d_big);
   dfree(d_cells); dfree(d_tscr); dfree(d_ctr); dfree(d_ull);
+  dfree(d_cell_base); dfree(d_lane_cells); dfree(d_unwind); dfree(d_lane_tscr);
   dfree(d_jobs); dfree(d_job_off); dfree(d_cnt); dfree(rc.raw); dfree(d_tables);
   TRACE("report: frees");
   return out;
