@@ -8,7 +8,7 @@ if os.environ.get("WITH_TORCH"):
 from damapper_b200 import synth, dazzdb, api
 
 api.init()
-contigs, rb, rl = synth.make_config("C2", scale=1.0, seed=7)
+contigs, rb, rl = synth.make_config("C2", scale=float(os.environ.get("SCALE", "1.0")), seed=7)
 rd = dazzdb.load_block((rb, rl)); rf = dazzdb.load_block(contigs)
 api.set_filter_params(20, 0, 4); api.set_options()
 hr, hg = api.HostBlock(*rd), api.HostBlock(*rf)
