@@ -77,8 +77,14 @@ __device__ __forceinline__ int slide8(const uint8_t *aseq, const uint8_t *bseq, 
 
 }  // namespace
 
+#ifndef PACK_MINB
+#define PACK_MINB 1
+#endif
+#ifndef PACK_BALLOT_TRIM
+#define PACK_BALLOT_TRIM 0
+#endif
 template <int G, bool DOB>
-__global__ void __launch_bounds__(PACK_WARPS * 32, 4)
+__global__ void __launch_bounds__(PACK_WARPS * 32, PACK_MINB)
 k_align_pack(AlignArgs A)
 { extern __shared__ int psm[];
   constexpr int W = PACK_W, SLOTW = PACK_SLOT_WORDS(DOB);
@@ -554,7 +560,7 @@ k_align_pack(AlignArgs A)
       // new band runs from the first to the last diagonal whose point is good enough; found with a
       // ballot over the new V values (the final besta of every slot is in its header by now)
       int tfirst = -1, tlast = -1;                       // owner: lane offsets within its band
-      for (int base = 0; base < total; base += 32)
+      for (int base = 0; PACK_BALLOT_TRIM && base < total; base += 32)
         { const int  j = base + lane;
           const bool act = (j < total);
           int g = 0;
@@ -596,7 +602,7 @@ k_align_pack(AlignArgs A)
           if (status != 0)
             phase = PH_JOBEND;
           else
-            { if (more == 0)                              // clipped at a sequence end: rare, serial
+            { if (more == 0 || !PACK_BALLOT_TRIM)         // clipped at a sequence end: rare, serial
                 { CLIP_AFTER_WAVE
                   const int n = besta - WAVE_LAG;
                   while (hgh >= low)
