@@ -197,9 +197,13 @@ def main():
         run_reference(args)
         return
 
+    # only the JSON line goes to the real stdout (NCCL and torchrun banners go to stderr)
+    real_out = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
-    from damapper_b200 import api, dazzdb
+    from damapper_b200 import api, dazzdb, shard
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -233,17 +237,12 @@ def main():
         """Reference index of the block's current orientation: built on rank 0, broadcast."""
         if world == 1:
             return api.Index(dref)
-        n = torch.zeros(1, dtype=torch.int64, device="cuda")
-        idx = None
+        idx, payload = None, None
         if rank == 0:
             idx = api.Index(dref)
-            n[0] = len(idx)
-        dist.broadcast(n, 0)
-        ln = int(n.item())
-        buf = torch.empty((ln + 2) * 16, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            L.damgpu_index_export(idx.h, buf.data_ptr())
-        dist.broadcast(buf, 0)
+            payload = torch.empty((len(idx) + 2) * 16, dtype=torch.uint8, device="cuda")
+            L.damgpu_index_export(idx.h, payload.data_ptr())
+        buf, ln = shard.broadcast_index(dist, torch, payload, "cuda", src=0)
         if rank == 0:
             return idx
         torch.cuda.synchronize()
@@ -384,7 +383,7 @@ def main():
                 out["cpu_baseline"] = cpu_baseline()
             except Exception as e:                       # the baseline must not take the line down
                 out["cpu_baseline"] = {"error": str(e)[:200]}
-        print(json.dumps(out))
+        os.write(real_out, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
