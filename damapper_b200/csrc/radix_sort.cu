@@ -14,7 +14,7 @@ constexpr int RS_THREADS = 384;
 constexpr int RS_ITEMS   = 12;
 constexpr int RS_TILE    = RS_THREADS * RS_ITEMS;      // records per tile (4608 = 72 KB staged)
 constexpr int RS_WARPS   = RS_THREADS / 32;
-constexpr int RS_PROBE   = 4;                          // predecessors fetched per look-back round
+constexpr int RS_PROBE   = 8;                          // predecessors fetched per look-back round
 constexpr int RS_SMEM    = RS_TILE * 16;               // dynamic shared memory per CTA
 
 // look-back word: [31:30] flag, [29:0] value
@@ -36,17 +36,24 @@ __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t *p)
 __device__ __forceinline__ void st_relaxed(uint32_t *p, uint32_t v)
 { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
 
-// lanes of the warp holding the same 8-bit digit: eight ballots (MATCH.ANY costs ~2.6x as much on
-// sm_100 when most of the 32 digits are distinct, measured: tools/sortlab.cu)
+// Lanes of the warp holding the same 8-bit digit: eight ballots (MATCH.ANY costs ~2.6x as much on
+// sm_100 when most of the 32 digits are distinct; tools/sortlab.cu).  The pass is bound by the ALU
+// pipe, so the loop is spelled out: per bit one AND+SETP (bit -> predicate), the VOTE, one SELP
+// and one LOP3 accumulating the lanes that differ from this one.
 __device__ __forceinline__ uint32_t match_digit(uint32_t dig)
-{ uint32_t m = 0xffffffffu;
+{ uint32_t diff = 0;
 #pragma unroll
   for (int b = 0; b < 8; b++)
-    { const bool     p = (dig >> b) & 1;
-      const uint32_t v = __ballot_sync(0xffffffffu, p);
-      m &= p ? v : ~v;
+    { uint32_t v, sx;
+      asm("{ .reg .pred p; .reg .b32 t;\n\t"
+          "and.b32 t, %2, %3;\n\t"
+          "setp.ne.u32 p, t, 0;\n\t"
+          "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+          "selp.b32 %1, 0xffffffff, 0, p;\n\t}"
+          : "=r"(v), "=r"(sx) : "r"(dig), "r"(1u << b));
+      diff |= v ^ sx;                                   // lanes whose bit b differs from mine
     }
-  return m;
+  return ~diff;
 }
 
 // ---- histogram of every pass byte in one read ---------------------------------------
@@ -108,10 +115,15 @@ __global__ void __launch_bounds__(256) k_radix_prefix(uint32_t *hist)
 //   6. thread d hands the run of digit d to the TMA engine (cp.async.bulk shared -> global:
 //      16-byte records make every run a legal bulk copy), no per-record store instructions.
 
+// W32 = 32-bit word of the record holding the key byte (compile time), psel = PRMT selector that
+// moves that byte to bits 0..7: the digit costs one instruction wherever it is needed.
+template <int W32>
 __global__ void __launch_bounds__(RS_THREADS, 2)
-k_radix_pass(const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t n, int byte,
+k_radix_pass(const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t n, uint32_t psel,
              const uint32_t *__restrict__ gbase, uint32_t *tile_state, uint32_t *tile_counter)
-{ extern __shared__ uint4 stage[];                    // 72 KB; the first 12 KB alias the counters
+{
+#define REC_DIGIT(r) __byte_perm((W32 == 0) ? (r).x : (W32 == 1) ? (r).y : (W32 == 2) ? (r).z : (r).w, 0, psel)
+  extern __shared__ uint4 stage[];                    // 72 KB; the first 12 KB alias the counters
   __shared__ uint32_t s_wsum[RS_WARPS];
   __shared__ uint32_t s_tile;
   uint32_t *whist = reinterpret_cast<uint32_t *>(stage);                 // [RS_WARPS][256]
@@ -129,18 +141,25 @@ k_radix_pass(const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t n, 
   const uint32_t tile   = s_tile;
   const uint32_t tbase  = tile * (uint32_t) RS_TILE;
   const uint32_t nvalid = (n - tbase < (uint32_t) RS_TILE) ? n - tbase : (uint32_t) RS_TILE;
-  const uint32_t base   = tbase + warp * (32 * RS_ITEMS) + lane;
+  const uint4 *src = in + tbase + warp * (32 * RS_ITEMS) + lane;
 
   uint4 rec[RS_ITEMS];
+  if (nvalid == (uint32_t) RS_TILE)                   // every tile but the last: no bounds tests
+    {
 #pragma unroll
-  for (int i = 0; i < RS_ITEMS; i++)                  // padding = all ones: digit 255, ranks after
-    { const uint32_t idx = base + i * 32;             // every real 255 of the (last) tile
-      rec[i] = (idx < n) ? __ldcs(in + idx)
-                         : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+      for (int i = 0; i < RS_ITEMS; i++)
+        rec[i] = __ldcs(src + i * 32);
+    }
+  else                                                // padding = all ones: digit 255, ranks after
+    { const uint32_t base = tbase + warp * (32 * RS_ITEMS) + lane;      // every real 255 of the tile
+#pragma unroll
+      for (int i = 0; i < RS_ITEMS; i++)
+        rec[i] = (base + i * 32 < n) ? __ldcs(src + i * 32)
+                                     : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
     }
 #pragma unroll
   for (int i = 0; i < RS_ITEMS; i++)
-    atomicAdd(&wh[rec_byte(rec[i], byte)], 1u);
+    atomicAdd(&wh[REC_DIGIT(rec[i])], 1u);
   __syncthreads();
 
   // digit d = tid (threads 256.. only take part in the barriers)
@@ -183,7 +202,7 @@ k_radix_pass(const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t n, 
   uint32_t pos[RS_ITEMS];
 #pragma unroll
   for (int i = 0; i < RS_ITEMS; i++)
-    { const uint32_t dig   = rec_byte(rec[i], byte);
+    { const uint32_t dig   = REC_DIGIT(rec[i]);
       const uint32_t peers = match_digit(dig);
       uint32_t old = 0;
       if ((peers & lt) == 0)
@@ -200,23 +219,26 @@ k_radix_pass(const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t n, 
   if (tid < 256)
     { uint32_t excl = 0;
       if (tile > 0)
-        { const uint32_t *col = tile_state + tid;
-          int64_t t = (int64_t) tile - 1;
-          bool done = false;
-          while (!done)
+        { const uint32_t *p = st - 256;                 // predecessor tile, same digit
+          uint32_t left = tile;
+          while (true)
             { uint32_t v[RS_PROBE];
 #pragma unroll
               for (int k = 0; k < RS_PROBE; k++)
-                v[k] = (t - k >= 0) ? ld_relaxed(col + (size_t) (t - k) * 256) : FLAG_INC;
-              int used = RS_PROBE;
+                v[k] = ((uint32_t) k < left) ? ld_relaxed(p - (size_t) k * 256) : FLAG_INC;
+              uint32_t adv = 0;
+              bool stop = false, inc = false;
 #pragma unroll
               for (int k = 0; k < RS_PROBE; k++)
-                if (!done && used == RS_PROBE)
-                  { if (v[k] & FLAG_INC)      { excl += v[k] & VAL_MASK; done = true; }
-                    else if (v[k] & FLAG_AGG) excl += v[k] & VAL_MASK;
-                    else                      used = k;          // not published yet: ask again
+                if (!stop)
+                  { if (v[k] == 0) stop = true;         // not published yet: ask again from here
+                    else
+                      { excl += v[k] & VAL_MASK; adv += 1;
+                        if (v[k] & FLAG_INC) { stop = true; inc = true; }
+                      }
                   }
-              t -= used;
+              if (inc) break;
+              p -= (size_t) adv * 256; left -= adv;
             }
           st_relaxed(st, FLAG_INC | (excl + cnt));
         }
@@ -231,6 +253,17 @@ k_radix_pass(const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t n, 
     }
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory may be released
+#undef REC_DIGIT
+}
+
+typedef void (*radix_pass_fn)(const uint4 *, uint4 *, uint32_t, uint32_t, const uint32_t *, uint32_t *, uint32_t *);
+static radix_pass_fn radix_pass_for(int byte)
+{ switch (byte >> 2)
+    { case 0:  return k_radix_pass<0>;
+      case 1:  return k_radix_pass<1>;
+      case 2:  return k_radix_pass<2>;
+      default: return k_radix_pass<3>;
+    }
 }
 
 void radix_histogram(const void *recs, uint32_t n, const int *bytes, int npass, uint32_t *hist,
@@ -257,15 +290,16 @@ void *radix_sort16(void *a, void *b, uint32_t n, const int *bytes, int npass, ui
 
   static bool attr_set = false;
   if (!attr_set)
-    { CUDA_CHECK(cudaFuncSetAttribute(k_radix_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM));
+    { for (int w = 0; w < 4; w++)
+        CUDA_CHECK(cudaFuncSetAttribute(radix_pass_for(4 * w), cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM));
       attr_set = true;
     }
   LAUNCH(k_radix_prefix, npass, 256, 0, stream, hist);
   uint4 *src = (uint4 *) a, *dst = (uint4 *) b;
   for (int p = 0; p < npass; p++)
     { CUDA_CHECK(cudaMemsetAsync(state, 0, sizeof(uint32_t) * ((size_t) ntiles * 256 + 1), stream));
-      LAUNCH(k_radix_pass, ntiles, RS_THREADS, RS_SMEM, stream, src, dst, n, bytes[p],
-             hist + p * 256, state, counter);
+      LAUNCH(radix_pass_for(bytes[p]), ntiles, RS_THREADS, RS_SMEM, stream, src, dst, n,
+             0x4440u | (uint32_t) (bytes[p] & 3), hist + p * 256, state, counter);
       uint4 *t = src; src = dst; dst = t;
     }
   CUDA_CHECK(cudaStreamSynchronize(stream));

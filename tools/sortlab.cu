@@ -743,6 +743,324 @@ k_pass_v4(const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t n, int
     }
 }
 
+template <int THREADS, int ITEMS, int BITS, int MATCHMODE, bool STAGED, int MINB, bool TMAST, int PROBE>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_pass_v7(const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t n, int word, int shift,
+          const uint32_t *__restrict__ gbase, uint32_t *tile_state, uint32_t *tile_counter)
+{ constexpr int NB = 1 << BITS, WARPS = THREADS / 32, TILE = THREADS * ITEMS;
+  constexpr int DPT = (NB + THREADS - 1) / THREADS;
+  extern __shared__ uint4 dyn[];
+  uint4    *stage = dyn;                                   // STAGED only; aliases the counters
+  uint32_t *whist = reinterpret_cast<uint32_t *>(dyn);     // [WARPS][NB]
+  __shared__ uint32_t s_dbase[STAGED ? NB : 1];
+  __shared__ uint32_t s_delta[NB];
+  __shared__ uint32_t s_wsum[WARPS];
+  __shared__ uint32_t s_tile;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lt = (1u << lane) - 1;
+  if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+  uint32_t *wh = whist + warp * NB;
+#pragma unroll
+  for (int i = lane; i < NB; i += 32) wh[i] = 0;
+  __syncthreads();
+  const uint32_t tile  = s_tile;
+  const uint32_t tbase = tile * (uint32_t) TILE;
+  const uint32_t nvalid = (n - tbase < (uint32_t) TILE) ? n - tbase : (uint32_t) TILE;
+  const uint32_t base = tbase + warp * (32 * ITEMS) + lane;
+
+  uint4 rec[ITEMS]; uint32_t rank[ITEMS];
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++)
+    { const uint32_t idx = base + i * 32;
+      rec[i] = (idx < n) ? __ldcs(in + idx) : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    }
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++)
+    { const uint32_t dig = rec_digit<BITS>(rec[i], word, shift);
+      const uint32_t peers = MATCHMODE ? match_ballot<BITS>(dig) : __match_any_sync(0xffffffffu, dig);
+      const uint32_t prev = wh[dig];
+      __syncwarp();
+      if ((peers & lt) == 0) wh[dig] = prev + (uint32_t) __popc(peers);
+      __syncwarp();
+      rank[i] = prev + __popc(peers & lt);
+    }
+  __syncthreads();                                         // (A)
+
+  uint32_t cnt[DPT], dbase[DPT], gdst[DPT];
+  { uint32_t tsum = 0;
+#pragma unroll
+    for (int j = 0; j < DPT; j++)
+      { const int d = tid * DPT + j;
+        uint32_t run = 0;
+        if (d < NB)
+          {
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) { uint32_t c = whist[w * NB + d]; whist[w * NB + d] = run; run += c; }
+            if (d == NB - 1) run -= (uint32_t) TILE - nvalid;
+            st_relaxed(tile_state + (size_t) tile * NB + d, (tile == 0 ? FLAG_INC : FLAG_AGG) | run);
+          }
+        cnt[j] = run; tsum += run;
+      }
+    if (STAGED)
+      { uint32_t x = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) s_wsum[warp] = x;
+        __syncthreads();                                   // (B1)
+        uint32_t add = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) if (w < warp) add += s_wsum[w];
+        uint32_t e = x + add - tsum;
+#pragma unroll
+        for (int j = 0; j < DPT; j++)
+          { const int d = tid * DPT + j;
+            dbase[j] = e;
+            if (d < NB) s_dbase[d] = e;
+            e += cnt[j];
+          }
+        __syncthreads();                                   // (B2)
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++)
+          { const uint32_t dig = rec_digit<BITS>(rec[i], word, shift);
+            rank[i] += s_dbase[dig] + wh[dig];
+          }
+        __syncthreads();                                   // (C) counters die, staging live
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) stage[rank[i]] = rec[i];
+        if (TMAST) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      }
+    else
+      {
+#pragma unroll
+        for (int j = 0; j < DPT; j++) dbase[j] = 0;
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < DPT; j++)
+    { const int d = tid * DPT + j;
+      if (d < NB)
+        { uint32_t excl = 0;
+          if (tile > 0)
+            { const uint32_t *col = tile_state + d;
+              int64_t t = (int64_t) tile - 1;
+              bool done = false;
+              while (!done)
+                { uint32_t v[PROBE];
+#pragma unroll
+                  for (int k = 0; k < PROBE; k++)
+                    v[k] = (t - k >= 0) ? ld_relaxed(col + (size_t) (t - k) * NB) : FLAG_INC;
+                  int used = PROBE;
+#pragma unroll
+                  for (int k = 0; k < PROBE; k++)
+                    if (!done && used == PROBE)
+                      { if (v[k] & FLAG_INC)      { excl += v[k] & VAL_MASK; done = true; }
+                        else if (v[k] & FLAG_AGG) excl += v[k] & VAL_MASK;
+                        else                      used = k;
+                      }
+                  t -= used;
+                }
+              st_relaxed(tile_state + (size_t) tile * NB + d, FLAG_INC | (excl + cnt[j]));
+            }
+          s_delta[d] = gbase[d] + excl - dbase[j];
+          gdst[j] = gbase[d] + excl;
+        }
+    }
+  __syncthreads();                                         // (D)
+  if (STAGED && TMAST)
+    {
+#pragma unroll
+      for (int j = 0; j < DPT; j++)
+        { const int d = tid * DPT + j;
+          if (d < NB && cnt[j] > 0)
+            { const uint32_t sa = (uint32_t) __cvta_generic_to_shared(stage + dbase[j]);
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                           :: "l"(out + gdst[j]), "r"(sa), "r"(cnt[j] * 16u) : "memory");
+            }
+        }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+  else if (STAGED)
+    {
+#pragma unroll
+      for (int i = 0; i < ITEMS; i++)
+        { const uint32_t j = tid + i * THREADS;
+          if (j < nvalid)
+            { const uint4 r = stage[j];
+              __stcs(out + (j + s_delta[rec_digit<BITS>(r, word, shift)]), r);
+            }
+        }
+    }
+  else
+    {
+#pragma unroll
+      for (int i = 0; i < ITEMS; i++)
+        { const uint32_t idx = base + i * 32;
+          const uint32_t dig = rec_digit<BITS>(rec[i], word, shift);
+          if (idx < n)
+            __stcs(out + (s_delta[dig] + wh[dig] + rank[i]), rec[i]);
+        }
+    }
+}
+
+// tuned ballot matcher: per bit one LOP3 (bit -> predicate), one VOTE, one SEL, one LOP3 (accumulate lanes that differ)
+template <int BITS> __device__ __forceinline__ uint32_t match_ballot2(uint32_t dig)
+{ uint32_t diff = 0;
+#pragma unroll
+  for (int b = 0; b < BITS; b++)
+    { uint32_t v, sx;
+      asm("{ .reg .pred p; .reg .b32 t;\n\t"
+          "and.b32 t, %2, %3;\n\t"
+          "setp.ne.u32 p, t, 0;\n\t"
+          "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+          "selp.b32 %1, 0xffffffff, 0, p;\n\t}"
+          : "=r"(v), "=r"(sx) : "r"(dig), "r"(1u << b));
+      diff |= v ^ sx;                                    // lanes whose bit b differs from mine
+    }
+  return ~diff;
+}
+
+// collision-table matcher: lanes publish their id under their digit; only digits held by several
+// lanes are resolved with ballots (about two per 32 random 8-bit digits)
+__device__ __forceinline__ uint32_t match_table(uint32_t dig, uint32_t *tag, int lane)
+{ tag[dig] = lane;
+  __syncwarp();
+  const uint32_t w = tag[dig];
+  __syncwarp();
+  uint32_t rem = __ballot_sync(0xffffffffu, w != (uint32_t) lane);
+  uint32_t peers = 1u << lane;
+  while (rem)
+    { const int l = __ffs(rem) - 1;
+      const uint32_t d0 = __shfl_sync(0xffffffffu, dig, l);
+      const uint32_t grp = __ballot_sync(0xffffffffu, dig == d0);
+      if (dig == d0) peers = grp;
+      rem &= ~grp;
+    }
+  return peers;
+}
+
+// ---------------- V9: v8 + PRMT digits (word as template), unchecked loads on full tiles, lean probe-8 look-back ----------------
+template <int THREADS, int ITEMS, int MINB, int PROBE, int W32>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_pass_v9(const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t n, uint32_t psel,
+          const uint32_t *__restrict__ gbase, uint32_t *tile_state, uint32_t *tile_counter)
+{ constexpr int NB = 256, WARPS = THREADS / 32, TILE = THREADS * ITEMS;
+  extern __shared__ uint4 dyn[];
+  uint4    *stage = dyn;
+  uint32_t *whist = reinterpret_cast<uint32_t *>(dyn);
+  __shared__ uint32_t s_wsum[WARPS];
+  __shared__ uint32_t s_tile;
+#define DIG9(r) __byte_perm((W32 == 0) ? (r).x : (W32 == 1) ? (r).y : (W32 == 2) ? (r).z : (r).w, 0, psel)
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lt = (1u << lane) - 1;
+  if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+  uint32_t *wh = whist + warp * NB;
+#pragma unroll
+  for (int i = lane; i < NB; i += 32) wh[i] = 0;
+  __syncthreads();
+  const uint32_t tile  = s_tile;
+  const uint32_t tbase = tile * (uint32_t) TILE;
+  const uint32_t nvalid = (n - tbase < (uint32_t) TILE) ? n - tbase : (uint32_t) TILE;
+  const uint4 *src = in + tbase + warp * (32 * ITEMS) + lane;
+
+  uint4 rec[ITEMS];
+  if (nvalid == (uint32_t) TILE)
+    {
+#pragma unroll
+      for (int i = 0; i < ITEMS; i++) rec[i] = __ldcs(src + i * 32);
+    }
+  else
+    { const uint32_t base = tbase + warp * (32 * ITEMS) + lane;
+#pragma unroll
+      for (int i = 0; i < ITEMS; i++)
+        rec[i] = (base + i * 32 < n) ? __ldcs(src + i * 32) : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    }
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++)
+    atomicAdd(&wh[DIG9(rec[i])], 1u);
+  __syncthreads();
+
+  uint32_t cnt = 0, dbase;
+  uint32_t *st = tile_state + (size_t) tile * 256 + (tid & 255);
+  if (tid < 256)
+    {
+#pragma unroll
+      for (int w = 0; w < WARPS; w++) cnt += whist[w * 256 + tid];
+      if (tid == 255) cnt -= (uint32_t) TILE - nvalid;
+      st_relaxed(st, (tile == 0 ? FLAG_INC : FLAG_AGG) | cnt);
+    }
+  { uint32_t x = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_wsum[warp] = x;
+    __syncthreads();
+    uint32_t add = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; w++) if (w < warp) add += s_wsum[w];
+    dbase = x + add - cnt;
+  }
+  if (tid < 256)
+    { uint32_t run = dbase;
+#pragma unroll
+      for (int w = 0; w < WARPS; w++) { const uint32_t c = whist[w * 256 + tid]; whist[w * 256 + tid] = run; run += c; }
+    }
+  __syncthreads();
+
+  uint32_t pos[ITEMS];
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++)
+    { const uint32_t dig   = DIG9(rec[i]);
+      const uint32_t peers = match_ballot2<8>(dig);
+      uint32_t old = 0;
+      if ((peers & lt) == 0) old = atomicAdd(&wh[dig], (uint32_t) __popc(peers));
+      pos[i] = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1) + __popc(peers & lt);
+    }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++) stage[pos[i]] = rec[i];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+
+  uint32_t gdst = 0;
+  if (tid < 256)
+    { uint32_t excl = 0;
+      if (tile > 0)
+        { const uint32_t *p = tile_state + (size_t) (tile - 1) * 256 + tid;
+          uint32_t left = tile;
+          while (true)
+            { uint32_t v[PROBE];
+#pragma unroll
+              for (int k = 0; k < PROBE; k++)
+                v[k] = ((uint32_t) k < left) ? ld_relaxed(p - (size_t) k * 256) : FLAG_INC;
+              uint32_t adv = 0; bool stop = false, inc = false;
+#pragma unroll
+              for (int k = 0; k < PROBE; k++)
+                if (!stop)
+                  { if (v[k] == 0) stop = true;                       // not published yet
+                    else
+                      { excl += v[k] & VAL_MASK; adv += 1;
+                        if (v[k] & FLAG_INC) { stop = true; inc = true; }
+                      }
+                  }
+              if (inc) break;
+              p -= (size_t) adv * 256; left -= adv;
+            }
+          st_relaxed(st, FLAG_INC | (excl + cnt));
+        }
+      gdst = gbase[tid] + excl;
+    }
+  __syncthreads();
+  if (tid < 256 && cnt > 0)
+    { const uint32_t sa = (uint32_t) __cvta_generic_to_shared(stage + dbase);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                   :: "l"(out + gdst), "r"(sa), "r"(cnt * 16u) : "memory");
+    }
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#undef DIG9
+}
+
 // ---------------- V5: early counts + ballot ranking straight to staged positions + probes + TMA store ----------------
 template <int THREADS, int ITEMS, int BITS, int MINB, int PROBE>
 __global__ void __launch_bounds__(THREADS, MINB)
@@ -822,6 +1140,139 @@ k_pass_v5(const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t n, int
   for (int i = 0; i < ITEMS; i++)
     { const uint32_t dig = rec_digit<BITS>(rec[i], word, shift);
       const uint32_t peers = match_ballot<BITS>(dig);
+      uint32_t old = 0;
+      if ((peers & lt) == 0) old = atomicAdd(&wh[dig], (uint32_t) __popc(peers));
+      pos[i] = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1) + __popc(peers & lt);
+    }
+  __syncthreads();                                         // (C) counters die, staging live
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++) stage[pos[i]] = rec[i];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+
+  uint32_t gdst[DPT];
+#pragma unroll
+  for (int j = 0; j < DPT; j++)
+    { const int d = tid * DPT + j;
+      if (d < NB)
+        { uint32_t excl = 0;
+          if (tile > 0)
+            { const uint32_t *col = tile_state + d;
+              int64_t t = (int64_t) tile - 1;
+              bool done = false;
+              while (!done)
+                { uint32_t v[PROBE];
+#pragma unroll
+                  for (int k = 0; k < PROBE; k++)
+                    v[k] = (t - k >= 0) ? ld_relaxed(col + (size_t) (t - k) * NB) : FLAG_INC;
+                  int used = PROBE;
+#pragma unroll
+                  for (int k = 0; k < PROBE; k++)
+                    if (!done && used == PROBE)
+                      { if (v[k] & FLAG_INC)      { excl += v[k] & VAL_MASK; done = true; }
+                        else if (v[k] & FLAG_AGG) excl += v[k] & VAL_MASK;
+                        else                      used = k;
+                      }
+                  t -= used;
+                }
+              st_relaxed(tile_state + (size_t) tile * NB + d, FLAG_INC | (excl + cnt[j]));
+            }
+          gdst[j] = gbase[d] + excl;
+        }
+    }
+  __syncthreads();                                         // (D)
+#pragma unroll
+  for (int j = 0; j < DPT; j++)
+    { const int d = tid * DPT + j;
+      if (d < NB && cnt[j] > 0)
+        { const uint32_t sa = (uint32_t) __cvta_generic_to_shared(stage + dbase[j]);
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                       :: "l"(out + gdst[j]), "r"(sa), "r"(cnt[j] * 16u) : "memory");
+        }
+    }
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// ---------------- V8 (v5 + matcher choice): early counts + ballot ranking straight to staged positions + probes + TMA store ----------------
+template <int THREADS, int ITEMS, int BITS, int MINB, int PROBE, int MM>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_pass_v8(const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t n, int word, int shift,
+          const uint32_t *__restrict__ gbase, uint32_t *tile_state, uint32_t *tile_counter)
+{ constexpr int NB = 1 << BITS, WARPS = THREADS / 32, TILE = THREADS * ITEMS;
+  constexpr int DPT = (NB + THREADS - 1) / THREADS;
+  extern __shared__ uint4 dyn[];
+  uint4    *stage = dyn;                                   // aliases the counters
+  uint32_t *whist = reinterpret_cast<uint32_t *>(dyn);     // [WARPS][NB]
+  __shared__ uint32_t s_wsum[WARPS];
+  __shared__ uint32_t s_tile;
+  __shared__ uint32_t s_tag[MM == 2 ? WARPS * 256 : 1];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lt = (1u << lane) - 1;
+  if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+  uint32_t *wh = whist + warp * NB;
+#pragma unroll
+  for (int i = lane; i < NB; i += 32) wh[i] = 0;
+  __syncthreads();
+  const uint32_t tile  = s_tile;
+  const uint32_t tbase = tile * (uint32_t) TILE;
+  const uint32_t nvalid = (n - tbase < (uint32_t) TILE) ? n - tbase : (uint32_t) TILE;
+  const uint32_t base = tbase + warp * (32 * ITEMS) + lane;
+
+  uint4 rec[ITEMS];
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++)
+    { const uint32_t idx = base + i * 32;
+      rec[i] = (idx < n) ? __ldcs(in + idx) : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    }
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++)
+    atomicAdd(&wh[rec_digit<BITS>(rec[i], word, shift)], 1u);
+  __syncthreads();                                         // (A)
+
+  uint32_t cnt[DPT], dbase[DPT];
+  { uint32_t tsum = 0;
+#pragma unroll
+    for (int j = 0; j < DPT; j++)
+      { const int d = tid * DPT + j;
+        uint32_t run = 0;
+        if (d < NB)
+          {
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) run += whist[w * NB + d];
+            if (d == NB - 1) run -= (uint32_t) TILE - nvalid;
+            st_relaxed(tile_state + (size_t) tile * NB + d, (tile == 0 ? FLAG_INC : FLAG_AGG) | run);
+          }
+        cnt[j] = run; tsum += run;
+      }
+    uint32_t x = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_wsum[warp] = x;
+    __syncthreads();                                       // (B1)
+    uint32_t add = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; w++) if (w < warp) add += s_wsum[w];
+    uint32_t e = x + add - tsum;
+#pragma unroll
+    for (int j = 0; j < DPT; j++)
+      { const int d = tid * DPT + j;
+        dbase[j] = e;
+        if (d < NB)
+          { uint32_t run = e;                              // per-warp counters become staged start positions
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) { uint32_t c = whist[w * NB + d]; whist[w * NB + d] = run; run += c; }
+          }
+        e += cnt[j];
+      }
+  }
+  __syncthreads();                                         // (B2)
+
+  uint32_t pos[ITEMS];
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++)
+    { const uint32_t dig = rec_digit<BITS>(rec[i], word, shift);
+      const uint32_t peers = (MM == 2) ? match_table(dig, s_tag + warp * 256, lane) : (MM == 1) ? match_ballot2<BITS>(dig) : match_ballot<BITS>(dig);
       uint32_t old = 0;
       if ((peers & lt) == 0) old = atomicAdd(&wh[dig], (uint32_t) __popc(peers));
       pos[i] = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1) + __popc(peers & lt);
@@ -1037,8 +1488,86 @@ __global__ void k_matchbench(uint32_t *outp, int iters)
   if (threadIdx.x == 0 && blockIdx.x == 0) outp[1 + MODE] = (uint32_t) ((t1 - t0) / iters);
 }
 
+// ---------------- skeleton study: staged copy, no ranking, no look-back ----------------
+// MODE 0: STG, identity   1: TMA runs, identity   2: TMA runs, 256-way scatter   3: STG, 256-way scatter
+// MODE 4: direct copy through registers (no smem), tile-structured
+template <int THREADS, int ITEMS, int MODE>
+__global__ void __launch_bounds__(THREADS)
+k_stage_copy(const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t n, uint32_t ntiles)
+{ constexpr int TILE = THREADS * ITEMS, RUN = TILE / 256;
+  extern __shared__ uint4 stage[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t tile = blockIdx.x, tbase = tile * (uint32_t) TILE;
+  const uint32_t base = tbase + warp * (32 * ITEMS) + lane;
+  uint4 rec[ITEMS];
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++)
+    { const uint32_t idx = base + i * 32;
+      rec[i] = (idx < n) ? __ldcs(in + idx) : make_uint4(0, 0, 0, 0);
+    }
+  if (MODE == 4)
+    {
+#pragma unroll
+      for (int i = 0; i < ITEMS; i++)
+        { const uint32_t idx = base + i * 32;
+          if (idx < n) __stcs(out + idx, rec[i]);
+        }
+      return;
+    }
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++)
+    stage[warp * (32 * ITEMS) + i * 32 + lane] = rec[i];
+  if (MODE == 1 || MODE == 2) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  const uint32_t per = (ntiles * (uint32_t) RUN);          // records per digit stream
+  if (MODE == 0 || MODE == 3)
+    {
+#pragma unroll
+      for (int i = 0; i < ITEMS; i++)
+        { const uint32_t j = tid + i * THREADS;
+          const uint32_t d = j / RUN, o = j % RUN;
+          const uint32_t dst = (MODE == 0) ? tbase + j : d * per + tile * RUN + o;
+          if (dst < n) __stcs(out + dst, stage[j]);
+        }
+    }
+  else
+    { if (tid < 256)
+        { const uint32_t d = tid;
+          const uint32_t dst = (MODE == 1) ? tbase + d * RUN : d * per + tile * RUN;
+          if (dst + RUN <= n)
+            { const uint32_t sa = (uint32_t) __cvta_generic_to_shared(stage + d * RUN);
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                           :: "l"(out + dst), "r"(sa), "r"((uint32_t) RUN * 16u) : "memory");
+            }
+        }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+}
+
 // ---------------- driver ----------------
 struct Ctx { uint4 *src, *a, *b; uint32_t n; uint32_t *hist, *state; unsigned long long *scal; int keybits; unsigned long long refsum; };
+
+template <int THREADS, int ITEMS, int MODE>
+static void run_stage(const char *name, Ctx &c)
+{ constexpr int TILE = THREADS * ITEMS;
+  const uint32_t ntiles = c.n / TILE;                      // whole tiles only
+  const uint32_t n = ntiles * TILE;
+  const size_t smem = (size_t) TILE * 16;
+  auto kern = k_stage_copy<THREADS, ITEMS, MODE>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  float best = 1e30f;
+  for (int r = 0; r < 5; r++)
+    { cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+      cudaEventRecord(e0); kern<<<ntiles, THREADS, smem>>>(c.src, c.a, n, ntiles); cudaEventRecord(e1);
+      CK(cudaEventSynchronize(e1)); CK(cudaGetLastError());
+      float ms; cudaEventElapsedTime(&ms, e0, e1); best = std::min(best, ms);
+    }
+  int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem);
+  printf("%-44s %.3f ms  %.0f GB/s (%.1f%%)  [%d CTAs/SM]\n", name, best, 32.0 * n / 1e6 / best, 100 * 32.0 * n / 1e6 / best / 6544.7, occ);
+  fflush(stdout);
+}
+
 
 static float run_timed(const char *name, Ctx &c, int bits, int npass, size_t tile, bool verify,
                        void (*launch)(Ctx &, const uint4 *, uint4 *, int word, int shift, uint32_t ntiles, int p))
@@ -1162,6 +1691,50 @@ static void L_v6(Ctx &c, const uint4 *s, uint4 *d, int word, int shift, uint32_t
   kern<<<ntiles, THREADS, smem>>>(s, d, c.n, word, shift, c.hist + p * NB, c.state, c.state + (size_t) ntiles * NB, c.scal + 8);
 }
 
+template <int THREADS, int ITEMS, int BITS, int MINB, bool TMAST, int PROBE>
+static void L_v7(Ctx &c, const uint4 *s, uint4 *d, int word, int shift, uint32_t ntiles, int p)
+{ constexpr int NB = 1 << BITS;
+  const size_t smem = std::max((size_t) (THREADS * ITEMS * 16), (size_t) (THREADS / 32) * NB * 4);
+  static bool set = false;
+  auto kern = k_pass_v7<THREADS, ITEMS, BITS, 1, true, MINB, TMAST, PROBE>;
+  if (!set) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); set = true;
+              int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem);
+              cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kern);
+              printf("  v7<%d,%d,%d,%d,tma=%d,probe=%d>: %d regs, %zu B dyn smem, %d CTAs/SM\n", THREADS, ITEMS, BITS, MINB, (int) TMAST, PROBE, fa.numRegs, smem, occ); }
+  kern<<<ntiles, THREADS, smem>>>(s, d, c.n, word, shift, c.hist + p * NB, c.state, c.state + (size_t) ntiles * NB);
+}
+
+template <int THREADS, int ITEMS, int BITS, int MINB, int PROBE, int MM>
+static void L_v8(Ctx &c, const uint4 *s, uint4 *d, int word, int shift, uint32_t ntiles, int p)
+{ constexpr int NB = 1 << BITS;
+  const size_t smem = std::max((size_t) (THREADS * ITEMS * 16), (size_t) (THREADS / 32) * NB * 4);
+  static bool set = false;
+  auto kern = k_pass_v8<THREADS, ITEMS, BITS, MINB, PROBE, MM>;
+  if (!set) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); set = true;
+              int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem);
+              cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kern);
+              printf("  v8<%d,%d,%d,%d,probe=%d,mm=%d>: %d regs, %zu B dyn smem, %d CTAs/SM\n", THREADS, ITEMS, BITS, MINB, PROBE, MM, fa.numRegs, smem, occ); }
+  kern<<<ntiles, THREADS, smem>>>(s, d, c.n, word, shift, c.hist + p * NB, c.state, c.state + (size_t) ntiles * NB);
+}
+
+template <int THREADS, int ITEMS, int MINB, int PROBE>
+static void L_v9(Ctx &c, const uint4 *s, uint4 *d, int word, int shift, uint32_t ntiles, int p)
+{ const size_t smem = (size_t) THREADS * ITEMS * 16;
+  const int byte = word * 8 + shift / 8, w32 = byte >> 2;
+  const uint32_t psel = 0x4440u | (uint32_t) (byte & 3);
+  static bool set = false;
+  if (!set)
+    { CK(cudaFuncSetAttribute(k_pass_v9<THREADS, ITEMS, MINB, PROBE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      CK(cudaFuncSetAttribute(k_pass_v9<THREADS, ITEMS, MINB, PROBE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      set = true;
+      int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pass_v9<THREADS, ITEMS, MINB, PROBE, 0>, THREADS, smem);
+      cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, k_pass_v9<THREADS, ITEMS, MINB, PROBE, 0>);
+      printf("  v9<%d,%d,%d,probe=%d>: %d regs, %zu B dyn smem, %d CTAs/SM\n", THREADS, ITEMS, MINB, PROBE, fa.numRegs, smem, occ);
+    }
+  if (w32 == 0) k_pass_v9<THREADS, ITEMS, MINB, PROBE, 0><<<ntiles, THREADS, smem>>>(s, d, c.n, psel, c.hist + p * 256, c.state, c.state + (size_t) ntiles * 256);
+  else          k_pass_v9<THREADS, ITEMS, MINB, PROBE, 1><<<ntiles, THREADS, smem>>>(s, d, c.n, psel, c.hist + p * 256, c.state, c.state + (size_t) ntiles * 256);
+}
+
 int main(int argc, char **argv)
 { uint32_t n = argc > 1 ? (uint32_t) atoll(argv[1]) : 139813248u;
   const char *which = argc > 2 ? argv[2] : "all";
@@ -1278,5 +1851,40 @@ int main(int argc, char **argv)
       const char *nm[9] = { "", "start->A (zero,load,hist,sync)", "A->B2 (scan,publish)", "B2->C (ballot rank, sync)", "C->staged (STS,fence)", "look-back", "sync D", "TMA issue", "TMA read wait" };
       for (int k = 1; k < 9; k++) printf("    %-34s %8.0f cycles/CTA\n", nm[k], t[k] / nt);
     }
+  if (want("sk"))
+    { run_stage<384, 12, 4>("sk 384x12 direct regs copy", c);
+      run_stage<384, 12, 0>("sk 384x12 staged STG identity", c);
+      run_stage<384, 12, 1>("sk 384x12 staged TMA identity", c);
+      run_stage<384, 12, 2>("sk 384x12 staged TMA scatter256", c);
+      run_stage<384, 12, 3>("sk 384x12 staged STG scatter256", c);
+      run_stage<256, 8, 4>("sk 256x8 direct regs copy", c);
+      run_stage<256, 8, 0>("sk 256x8 staged STG identity", c);
+      run_stage<256, 8, 2>("sk 256x8 staged TMA scatter256", c);
+      run_stage<512, 8, 2>("sk 512x8 staged TMA scatter256", c);
+      run_stage<512, 16, 2>("sk 512x16 staged TMA scatter256", c);
+      run_stage<256, 16, 2>("sk 256x16 staged TMA scatter256", c);
+      run_stage<1024, 8, 2>("sk 1024x8 staged TMA scatter256", c);
+    }
+  if (want("v7a")) run_timed("v7 512x8 tma probe4 rmw", c, 8, 5, 4096, true, L_v7<512, 8, 8, 2, true, 4>);
+  if (want("v7b")) run_timed("v7 384x12 tma probe4 rmw", c, 8, 5, 4608, true, L_v7<384, 12, 8, 2, true, 4>);
+  if (want("v7c")) run_timed("v7 384x8 tma probe4 rmw", c, 8, 5, 3072, true, L_v7<384, 8, 8, 3, true, 4>);
+  if (want("v7d")) run_timed("v7 256x16 tma probe4 rmw", c, 8, 5, 4096, true, L_v7<256, 16, 8, 2, true, 4>);
+  if (want("v7e")) run_timed("v7 256x12 tma probe4 rmw", c, 8, 5, 3072, true, L_v7<256, 12, 8, 3, true, 4>);
+  if (want("v7f")) run_timed("v4 384x12 tma probe4 atomics", c, 8, 5, 4608, true, L_v4<384, 12, 8, 2, true, 4>);
+  if (want("v8a")) run_timed("v8 384x12 ballot (ref)", c, 8, 5, 4608, true, L_v8<384, 12, 8, 2, 4, 0>);
+  if (want("v8b")) run_timed("v8 384x12 ballot2 tuned", c, 8, 5, 4608, true, L_v8<384, 12, 8, 2, 4, 1>);
+  if (want("v8c")) run_timed("v8 384x12 table matcher", c, 8, 5, 4608, true, L_v8<384, 12, 8, 2, 4, 2>);
+  if (want("v8d")) run_timed("v8 384x8 ballot2 tuned", c, 8, 5, 3072, true, L_v8<384, 8, 8, 3, 4, 1>);
+  if (want("v8e")) run_timed("v8 384x8 table matcher", c, 8, 5, 3072, true, L_v8<384, 8, 8, 3, 4, 2>);
+  if (want("v8f")) run_timed("v8 512x8 table matcher", c, 8, 5, 4096, true, L_v8<512, 8, 8, 2, 4, 2>);
+  if (want("v8g")) run_timed("v8 256x16 table matcher", c, 8, 5, 4096, true, L_v8<256, 16, 8, 2, 4, 2>);
+  if (want("v8h")) run_timed("v8 256x12 table matcher", c, 8, 5, 3072, true, L_v8<256, 12, 8, 3, 4, 2>);
+  if (want("v9a")) run_timed("v9 384x12 probe8", c, 8, 5, 4608, true, L_v9<384, 12, 2, 8>);
+  if (want("v9b")) run_timed("v9 384x12 probe4", c, 8, 5, 4608, true, L_v9<384, 12, 2, 4>);
+  if (want("v9c")) run_timed("v9 384x8 probe8", c, 8, 5, 3072, true, L_v9<384, 8, 3, 8>);
+  if (want("v9d")) run_timed("v9 512x8 probe8", c, 8, 5, 4096, true, L_v9<512, 8, 2, 8>);
+  if (want("v9e")) run_timed("v9 256x12 probe8", c, 8, 5, 3072, true, L_v9<256, 12, 3, 8>);
+  if (want("v9f")) run_timed("v9 256x16 probe8", c, 8, 5, 4096, true, L_v9<256, 16, 2, 8>);
+  if (want("v9g")) run_timed("v9 384x12 probe16", c, 8, 5, 4608, true, L_v9<384, 12, 2, 16>);
   return 0;
 }
