@@ -45,6 +45,7 @@ SYMBOLS = {
     "damgpu_last_error": (C.c_char_p, []),
     "damgpu_launch_count": (C.c_uint64, []),
     "damgpu_time_kernels": (None, [C.c_int]),
+    "damgpu_set_align_tier": (None, [C.c_int, C.c_int]),
     "damgpu_last_sort_times": (None, [C.POINTER(C.c_float)]),
     "damgpu_Set_Filter_Params": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "damgpu_Sort_Kmers": (_P, [C.POINTER(CBlock), C.POINTER(C.c_int)]),

@@ -390,7 +390,7 @@ k_align_pack(AlignArgs A)
       if (phase == PH_WAVE)
         { bool go = more && (lasta >= besta - TRIM_MLAG);
           if (go && hgh < low)                            // empty band: the reference would read
-            { nempty += 1; go = false; }                  // stale cells; stop (as oracle and align.cu)
+            { nempty += 1; go = false; }                  // stale cells; stop (as align.cu does)
           if (go && hgh - low + 6 > W)
             { status = LERR_BAND; go = false; }
           if (!go)

@@ -162,6 +162,10 @@ void damgpu_set_fatal(void (*clean_exit)(int)) { g_clean_exit = clean_exit; }
 const char *damgpu_last_error(void) { return g_last_error.c_str(); }
 uint64_t damgpu_launch_count(void) { return g_launches; }
 void damgpu_time_kernels(int on) { g_time_kernels = (on != 0); }
+void damgpu_set_align_tier(int tier, int slots)
+{ g_align_tier = (tier < 0 || tier > 2) ? 0 : tier;
+  g_align_slots = (slots == 2 || slots == 8) ? slots : 4;
+}
 void damgpu_last_sort_times(float out[3]) { out[0] = g_sort_times[0]; out[1] = g_sort_times[1]; out[2] = g_sort_times[2]; }
 
 int damgpu_Set_Filter_Params(int kmer, int suppress, int nthreads)   // map.c:124-150

@@ -71,6 +71,30 @@ def test_pipeline_matches_oracle(api, oracle_mod, cfg, scale, seed, kw):
     _gpu_vs_oracle(api, oracle_mod, cfg, scale, seed, **kw)
 
 
+@pytest.mark.parametrize("tier,slots", [(2, 4), (2, 8), (2, 2), (1, 4)])
+@pytest.mark.parametrize("cfg,scale,seed,kw", [
+    ("C1", 0.1, 41, dict(do_b=1, profile=1)),
+    ("C5", 0.1, 42, dict(do_b=1)),            # wide bands: many jobs fall through to the warp kernel
+    ("C3", 0.004, 43, dict(best_tie=0.9)),
+])
+def test_alignment_tiers_give_the_same_records(api, oracle_mod, tier, slots, cfg, scale, seed, kw):
+    """pack (G jobs per warp) and lane (thread per job) tiers + k_unwind vs the oracle; the wave
+    statistics are not compared because handed-off jobs are counted twice."""
+    contigs, rb, rl, rd, rf, rc = make_case(cfg, scale, seed)
+    freq = base_freq(contigs)
+    o = oracle_mod.map_block(oracle_mod.HostBlock(*rd), [(oracle_mod.HostBlock(*rf), oracle_mod.HostBlock(*rc))],
+                             oracle_mod.HostBlock(*rf), freq=freq, **kw)
+    L = api.load()
+    L.damgpu_set_align_tier(tier, slots)
+    try:
+        g = api.map_block(api.HostBlock(*rd), [api.HostBlock(*rf)], api.HostBlock(*rf), freq=freq, **kw)
+    finally:
+        L.damgpu_set_align_tier(0, 4)
+    assert g["a"] == o["a"], "M records differ"
+    assert g["b"] == o["b"], "R records differ"
+    assert g["prof"] == o["prof"], "-p track differs"
+
+
 @pytest.mark.parametrize("cfg,scale,seed,kmer,suppress", [
     ("C1", 0.1, 4, 20, 0), ("C3", 0.002, 5, 14, 0), ("C1", 0.05, 6, 16, 10),
     ("C5", 0.1, 7, 32, 0), ("C1", 0.05, 8, 12, 0), ("C1", 0.05, 9, 9, 3),
