@@ -253,6 +253,23 @@ def test_full_size_properties(api):
     assert out["stats"]["overflow_jobs"] == 0 or out["stats"]["overflow_jobs"] < 50
 
 
+def test_full_size_c2_matches_oracle(api, oracle_mod):
+    """BASELINE config 2 at FULL size (4.6 Mbp + 13.8 k reads, the bench workload): every M and R
+    record and the -p track bit for bit against the oracle (about half a minute of one host core)."""
+    contigs, rb, rl, rd, rf, rc = make_case("C2", 1.0, 7)
+    freq = base_freq(contigs)
+    kw = dict(do_b=1, profile=1)
+    o = oracle_mod.map_block(oracle_mod.HostBlock(*rd), [(oracle_mod.HostBlock(*rf), oracle_mod.HostBlock(*rc))],
+                             oracle_mod.HostBlock(*rf), freq=freq, **kw)
+    g = api.map_block(api.HostBlock(*rd), [api.HostBlock(*rf)], api.HostBlock(*rf), freq=freq, **kw)
+    assert g["anrec"] == o["anrec"] > 13000
+    assert g["a"] == o["a"], "M records differ"
+    assert g["b"] == o["b"], "R records differ"
+    assert g["prof"] == o["prof"], "-p track differs"
+    for key in ("nalign", "nwaves", "ncells"):
+        assert g["stats"][key] == o["stats"][key], key
+
+
 def test_host_driver_cli(api, tmp_path):
     """The C host driver (damapper_b200/damapper): reference command line, DAZZ_DB input read
     by its own loader, per-thread .las + .prof output equal to the reference's golden stream."""
