@@ -89,6 +89,7 @@ struct AlignArgs
 
 void launch_align(const AlignArgs &A, bool big, int nblocks, cudaStream_t stream);
 void launch_align_pack(const AlignArgs &A, int njobs, cudaStream_t stream);
+void launch_align_group(const AlignArgs &A, int njobs, cudaStream_t stream);
 int  lane_warps(bool dob);
 void launch_align_lane(const AlignArgs &A, int nblocks, cudaStream_t stream);
 void launch_unwind(const AlignArgs &A, int max_alns, cudaStream_t stream);

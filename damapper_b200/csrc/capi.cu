@@ -145,7 +145,7 @@ int damgpu_init(int device)
   g_sms = prop.multiProcessorCount;
   g_trace = (getenv("DAMGPU_TRACE") != nullptr);
   if (const char *t = getenv("DAMGPU_ALIGN"))
-    g_align_tier = !strcmp(t, "warp") ? 0 : !strcmp(t, "lane") ? 1 : 2;
+    g_align_tier = !strcmp(t, "warp") ? 0 : !strcmp(t, "lane") ? 1 : !strcmp(t, "group") ? 3 : 2;
   if (const char *t = getenv("DAMGPU_SLOTS"))
     g_align_slots = atoi(t);
   g_ready = true;
@@ -163,7 +163,7 @@ const char *damgpu_last_error(void) { return g_last_error.c_str(); }
 uint64_t damgpu_launch_count(void) { return g_launches; }
 void damgpu_time_kernels(int on) { g_time_kernels = (on != 0); }
 void damgpu_set_align_tier(int tier, int slots)
-{ g_align_tier = (tier < 0 || tier > 2) ? 0 : tier;
+{ g_align_tier = (tier < 0 || tier > 3) ? 0 : tier;
   g_align_slots = (slots == 2 || slots == 8) ? slots : 4;
 }
 void damgpu_last_sort_times(float out[3]) { out[0] = g_sort_times[0]; out[1] = g_sort_times[1]; out[2] = g_sort_times[2]; }

@@ -726,7 +726,11 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   if (g_time_kernels)
     { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, stream); }
   if (njobs > 0)
-    { if (g_align_tier == 2)
+    { if (g_align_tier == 3)
+        { launch_align_group(A, njobs, stream);
+          launch_unwind(A, aln_cap, stream);
+        }
+      else if (g_align_tier == 2)
         { launch_align_pack(A, njobs, stream);
           launch_unwind(A, aln_cap, stream);
         }

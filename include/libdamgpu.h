@@ -75,7 +75,8 @@ const char *damgpu_last_error(void);
 uint64_t damgpu_launch_count(void);                   /* kernels launched so far            */
 void damgpu_time_kernels(int on);                     /* record per-phase CUDA-event times  */
 /* first tier of the alignment phase: 0 = warp per candidate (default), 1 = thread per candidate,
-   2 = `slots` candidates per warp with their diagonals packed onto the lanes (slots 2, 4 or 8);
+   2 = `slots` candidates per warp with their diagonals packed onto the lanes (slots 2, 4 or 8),
+   3 = `slots` candidates per warp, each owned by a fixed group of 32/slots lanes;
    every tier yields the same records (Local_Alignment, align.c:1727-1946) */
 void damgpu_set_align_tier(int tier, int slots);
 /* ms of the last Sort_Kmers: [0]=extraction kernel, [1]=all radix passes, [2]=#passes */

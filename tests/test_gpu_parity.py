@@ -71,14 +71,15 @@ def test_pipeline_matches_oracle(api, oracle_mod, cfg, scale, seed, kw):
     _gpu_vs_oracle(api, oracle_mod, cfg, scale, seed, **kw)
 
 
-@pytest.mark.parametrize("tier,slots", [(2, 4), (2, 8), (2, 2), (1, 4)])
+@pytest.mark.parametrize("tier,slots", [(2, 4), (2, 8), (2, 2), (1, 4), (3, 2), (3, 4)])
 @pytest.mark.parametrize("cfg,scale,seed,kw", [
     ("C1", 0.1, 41, dict(do_b=1, profile=1)),
     ("C5", 0.1, 42, dict(do_b=1)),            # wide bands: many jobs fall through to the warp kernel
     ("C3", 0.004, 43, dict(best_tie=0.9)),
 ])
 def test_alignment_tiers_give_the_same_records(api, oracle_mod, tier, slots, cfg, scale, seed, kw):
-    """pack (G jobs per warp) and lane (thread per job) tiers + k_unwind vs the oracle; the wave
+    """pack (G jobs per warp, packed lanes), lane (thread per job) and group (G jobs per warp, fixed
+    lane groups) tiers + k_unwind vs the oracle; the wave
     statistics are not compared because handed-off jobs are counted twice."""
     contigs, rb, rl, rd, rf, rc = make_case(cfg, scale, seed)
     freq = base_freq(contigs)
