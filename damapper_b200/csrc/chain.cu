@@ -7,6 +7,7 @@
 // sorted slice of a global scratch array (slot i of every scratch array belongs to seed i,
 // hence no per-thread sizing).  Candidates and their Jump lists persist in device pools
 // across Match_Filter calls; per-read list heads replace DAZZ_READ.coff (map.c:1875).
+#include <algorithm>
 #include "common.cuh"
 #include "mapper.cuh"
 
@@ -301,9 +302,13 @@ k_chain(const SeedPair *__restrict__ hits, int64_t nhits, int nreads, int K, int
 static void ensure_pools(Mapper *m, int64_t nhits)
 { // a candidate is the best end of a distinct chain origin with >= 3 seeds and the from-paths
   // of distinct origins are disjoint: at most nhits/3 new candidates and nhits new jumps
-  int h_ctop = 0; unsigned long long h_jtop = 0;
-  CUDA_CHECK(cudaMemcpy(&h_ctop, m->cand_top, sizeof(int), cudaMemcpyDeviceToHost));
-  CUDA_CHECK(cudaMemcpy(&h_jtop, m->jump_top, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  // Upper bounds kept on the host (no read-back): every call adds at most nhits/3 candidates and
+  // nhits jumps.  The true tops are fetched only when a pool has to grow.
+  int h_ctop = m->ctop_bound; unsigned long long h_jtop = m->jtop_bound;
+  if ((int64_t) h_ctop + nhits / 3 + 16 > m->cand_cap || h_jtop + (uint64_t) nhits + 16 > m->jump_cap)
+    { CUDA_CHECK(cudaMemcpy(&h_ctop, m->cand_top, sizeof(int), cudaMemcpyDeviceToHost));
+      CUDA_CHECK(cudaMemcpy(&h_jtop, m->jump_top, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    }
   int64_t need_c = (int64_t) h_ctop + nhits / 3 + 16;
   uint64_t need_j = h_jtop + (uint64_t) nhits + 16;
   if (need_c > 0x7ffffff0ll)
@@ -325,6 +330,8 @@ static void ensure_pools(Mapper *m, int64_t nhits)
       dfree(m->jumps);
       m->jumps = nj; m->jump_cap = cap;
     }
+  m->ctop_bound = (int) std::min<int64_t>(need_c, 0x7ffffff0ll);
+  m->jtop_bound = need_j;
 }
 
 Mapper *mapper_new(const DeviceBlock *reads)
@@ -357,6 +364,7 @@ void mapper_reset(Mapper *m)                           // start != 0, map.c:1574
   CUDA_CHECK(cudaMemset(m->cand_top, 0, sizeof(int) * 4));
   CUDA_CHECK(cudaMemset(m->jump_top, 0, sizeof(unsigned long long) * 2));
   CUDA_CHECK(cudaMemset(m->overflow, 0, sizeof(int)));
+  m->ctop_bound = 0; m->jtop_bound = 0;
   CUDA_CHECK(cudaMemset(m->cover, 0, sizeof(int16_t) * ((size_t) m->h_coff[n] + 2)));
 }
 
@@ -384,13 +392,10 @@ void chain_seeds(Mapper *m, const SeedSet *ss, int bstart, int comp, cudaStream_
   LAUNCH(k_chain, (n + CH_WARPS - 1) / CH_WARPS, CH_WARPS * 32, 0, stream, ss->hits, nhits, n, g_par.kmer, bstart, comp,
          g_par.profile, g_par.spacing, sc, m->cand, m->cand_top, m->cand_cap, m->jumps,
          m->jump_top, (unsigned long long) m->jump_cap, m->head, m->cover, m->coff, m->overflow);
-  int ovf = 0;
-  CUDA_CHECK(cudaMemcpyAsync(&ovf, m->overflow, sizeof(int), cudaMemcpyDeviceToHost, stream));
-  CUDA_CHECK(cudaStreamSynchronize(stream));
-  dfree(scratch); dfree(sc.S);
+  dfree(scratch); dfree(sc.S);                        // stream-ordered: reused only by later launches
   TRACE("chain: kernel");
-  if (ovf)
-    fatal("Match_Filter: candidate/jump pool overflow (internal sizing error)");
+  // m->overflow (internal sizing error, cannot happen with the bounds above) is checked by the
+  // Reporter, which has to synchronise anyway
 }
 
 }  // namespace damgpu

@@ -404,7 +404,6 @@ KmerIndex *sort_kmers(const DeviceBlock *blk, int K, int suppress, cudaStream_t 
       return idx;
     }
   LAUNCH(k_set_sentinels, 1, 1, 0, stream, rez, (int64_t) kept);
-  CUDA_CHECK(cudaStreamSynchronize(stream));
   TRACE("sort_kmers: tail");
   idx->list = rez;
   idx->len  = (int) kept;

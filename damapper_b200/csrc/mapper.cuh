@@ -40,6 +40,8 @@ struct Mapper
   int64_t   *coff = nullptr;                 // per-read offset into cover
   std::vector<int64_t> h_coff;
   int       *overflow = nullptr;
+  int        ctop_bound = 0;                 // host-side upper bounds of *cand_top / *jump_top
+  unsigned long long jtop_bound = 0;
   int        spacing = 0;
   int64_t    last_nhits = 0;
   int        last_limit = 0;

@@ -302,8 +302,7 @@ void *radix_sort16(void *a, void *b, uint32_t n, const int *bytes, int npass, ui
              0x4440u | (uint32_t) (bytes[p] & 3), hist + p * 256, state, counter);
       uint4 *t = src; src = dst; dst = t;
     }
-  CUDA_CHECK(cudaStreamSynchronize(stream));
-  dfree(state);
+  dfree(state);                                        // stream-ordered reuse (cache_alloc)
   return src;
 }
 

@@ -659,6 +659,11 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   int *d_cnt = dalloc<int>(n + 1);
   LAUNCH(k_count_cands, (n + 255) / 256, 256, 0, stream, m->head, m->cand, n, d_cnt);
   std::vector<int> cnt = d2h(d_cnt, n);
+  { int ovf = 0;                                         // deferred check of the chain kernels
+    CUDA_CHECK(cudaMemcpy(&ovf, m->overflow, sizeof(int), cudaMemcpyDeviceToHost));
+    if (ovf)
+      fatal("Match_Filter: candidate/jump pool overflow (internal sizing error)");
+  }
   std::vector<int64_t> job_off(n + 1);
   int64_t njobs64 = 0;
   for (int i = 0; i < n; i++) { job_off[i] = njobs64; njobs64 += cnt[i]; }

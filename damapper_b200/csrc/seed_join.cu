@@ -150,9 +150,10 @@ k_join_match(const KmerPos *__restrict__ A, int alen, const KmerPos *__restrict_
 
 // ---- histogram of run products (count_thread, map.c:919-927) ------------------------------
 __global__ void __launch_bounds__(256)
-k_run_histogram(const Run *__restrict__ runs, uint32_t nruns, unsigned long long *gram,
-                unsigned long long *total)
+k_run_histogram(const Run *__restrict__ runs, const uint32_t *__restrict__ nruns_p,
+                unsigned long long *gram, unsigned long long *total)
 { __shared__ uint32_t sh[2048];
+  const uint32_t nruns = *nruns_p;
   for (int i = threadIdx.x; i < 2048; i += 256) sh[i] = 0;
   __syncthreads();
   unsigned long long sum = 0;
@@ -336,25 +337,22 @@ SeedSet *merge_join(const KmerIndex *aidx, const DeviceBlock *ablock, const Kmer
   Run *runs = dalloc<Run>((size_t) dlen + 1);
   LAUNCH(k_join_match, ntiles, JM_THREADS, 0, stream, D, dlen, T, tlen, lut, shift, swap ? 1 : 0,
          runs, state, counter, counter + 1);
-  uint32_t nruns = 0;
-  CUDA_CHECK(cudaMemcpyAsync(&nruns, counter + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-
   TRACE("join: lut+match launch");
+  // histogram of the run products; the run count stays on the device until both are read back
   unsigned long long *gram = dalloc<unsigned long long>(MAXGRAM + 1);
   CUDA_CHECK(cudaMemsetAsync(gram, 0, sizeof(unsigned long long) * (MAXGRAM + 1), stream));
-  CUDA_CHECK(cudaStreamSynchronize(stream));
-  if (!swap) dfree(lut);
-  dfree(state);
-
-  if (nruns > 0)
-    { int grid = (int) ((nruns + 255) / 256);
-      if (grid > sm_count() * 8) grid = sm_count() * 8;
-      LAUNCH(k_run_histogram, grid, 256, 0, stream, runs, nruns, gram, gram + MAXGRAM);
-    }
+  { int grid = (int) (((int64_t) dlen + 255) / 256);
+    if (grid > sm_count() * 8) grid = sm_count() * 8;
+    LAUNCH(k_run_histogram, grid, 256, 0, stream, runs, counter + 1, gram, gram + MAXGRAM);
+  }
+  uint32_t nruns = 0;
   ss->histo.resize(MAXGRAM + 1);
+  CUDA_CHECK(cudaMemcpyAsync(&nruns, counter + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
   CUDA_CHECK(cudaMemcpyAsync(ss->histo.data(), gram, sizeof(unsigned long long) * (MAXGRAM + 1),
                              cudaMemcpyDeviceToHost, stream));
   CUDA_CHECK(cudaStreamSynchronize(stream));
+  if (!swap) dfree(lut);
+  dfree(state);
   dfree(gram);
 
   TRACE("join: match sync+histogram");
@@ -410,7 +408,6 @@ SeedSet *merge_join(const KmerIndex *aidx, const DeviceBlock *ablock, const Kmer
   TRACE("join: emit");
   SeedPair *rez = (SeedPair *) radix_sort16(h1, h2, (uint32_t) nhits, bytes, npass, hist, stream);
   LAUNCH(k_seed_sentinel, 1, 1, 0, stream, rez, nhits);
-  CUDA_CHECK(cudaStreamSynchronize(stream));
   dfree(rez == h1 ? h2 : h1);
   dfree(hist); dfree(off); dfree(runs);
   TRACE("join: seed sort");
