@@ -50,6 +50,7 @@ SYMBOLS = {
     "damgpu_Set_Filter_Params": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "damgpu_Sort_Kmers": (_P, [C.POINTER(CBlock), C.POINTER(C.c_int)]),
     "damgpu_block_upload": (_P, [C.POINTER(CBlock)]),
+    "damgpu_block_upload_packed": (_P, [C.POINTER(CBlock), C.c_void_p, C.c_void_p, C.c_int64]),
     "damgpu_block_free": (None, [_P]),
     "damgpu_block_complement": (None, [_P]),
     "damgpu_block_download_bases": (None, [_P, _P]),
@@ -150,10 +151,29 @@ def set_options(verbose=0, profile=0, spacing=100, best_tie=1.0, sort_path="/tmp
     load().damgpu_set_options(C.byref(o))
 
 
+def pack_bps(hb: "HostBlock"):
+    """The block as the .bps file holds it: (packed bytes, per-read byte offsets); four bases per
+    byte, first base in the two top bits (reference DB.c:319-340)."""
+    chunks, poff, o = [], np.zeros(hb.nreads, dtype=np.int64), 0
+    for i in range(hb.nreads):
+        s = hb.bases[1 + int(hb.boff[i]): 1 + int(hb.boff[i]) + int(hb.rlen[i])]
+        pad = (-s.size) % 4
+        q = np.concatenate([s, np.zeros(pad, dtype=np.uint8)]).reshape(-1, 4)
+        chunks.append(((q[:, 0] << 6) | (q[:, 1] << 4) | (q[:, 2] << 2) | q[:, 3]).astype(np.uint8))
+        poff[i] = o
+        o += chunks[-1].size
+    packed = np.concatenate(chunks) if chunks else np.zeros(0, dtype=np.uint8)
+    return np.ascontiguousarray(packed), poff
+
+
 class DeviceBlock:
-    def __init__(self, hb: HostBlock):
+    def __init__(self, hb: HostBlock, packed: bool = False):
         self.host = hb
-        self.h = init().damgpu_block_upload(C.byref(hb.c))
+        if packed:
+            pk, poff = pack_bps(hb)
+            self.h = init().damgpu_block_upload_packed(C.byref(hb.c), pk.ctypes.data, poff.ctypes.data, pk.size)
+        else:
+            self.h = init().damgpu_block_upload(C.byref(hb.c))
 
     def complement(self):
         load().damgpu_block_complement(self.h)

@@ -187,6 +187,16 @@ damgpu_dblock *damgpu_block_upload(const damgpu_block *block)
   return reinterpret_cast<damgpu_dblock *>(upload(block));
 }
 
+damgpu_dblock *damgpu_block_upload_packed(const damgpu_block *b, const uint8_t *packed,
+                                          const int64_t *poff, int64_t packed_bytes)
+{ need_gpu();
+  if (b->nreads > 0 && (packed == nullptr || poff == nullptr))
+    fatal("damgpu_block_upload_packed: no packed image");
+  return reinterpret_cast<damgpu_dblock *>(
+      upload_block_packed(packed, poff, packed_bytes, b->boff, b->rlen, b->nreads, b->tfirst,
+                          b->maxlen, b->totlen, b->sizeof_db, 0));
+}
+
 void damgpu_block_free(damgpu_dblock *blk) { free_block(reinterpret_cast<DeviceBlock *>(blk)); }
 
 void damgpu_block_complement(damgpu_dblock *blk)

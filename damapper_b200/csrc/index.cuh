@@ -34,6 +34,10 @@ struct KmerIndex
 DeviceBlock *upload_block(const uint8_t *bases, const int64_t *boff, const int32_t *rlen,
                           int nreads, int tfirst, int maxlen, int64_t totlen, int64_t sizeof_db,
                           cudaStream_t stream);
+// the same block from its .bps image (2 bits per base), expanded on the device
+DeviceBlock *upload_block_packed(const uint8_t *packed, const int64_t *poff, int64_t packed_bytes,
+                                 const int64_t *boff, const int32_t *rlen, int nreads, int tfirst,
+                                 int maxlen, int64_t totlen, int64_t sizeof_db, cudaStream_t stream);
 void         free_block(DeviceBlock *blk);
 // complement_DB(block, inplace) of the reference driver (damapper.c:433-469), on the device
 void         complement_block(DeviceBlock *blk, cudaStream_t stream);

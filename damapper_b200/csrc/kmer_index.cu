@@ -256,6 +256,65 @@ DeviceBlock *upload_block(const uint8_t *bases, const int64_t *boff, const int32
   return blk;
 }
 
+// .bps -> Load_All_Reads image (Uncompress_Read DB.c:342-363 + the 4 separators of DB.c:1402-1433),
+// one warp per read: lane l expands packed byte 32*i + l into the four bases it holds.
+__global__ void __launch_bounds__(256)
+k_unpack_bps(const uint8_t *__restrict__ packed, const int64_t *__restrict__ poff,
+             const int64_t *__restrict__ boff, int nreads, uint8_t *__restrict__ bases)
+{ const int lane = threadIdx.x & 31;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nreads; r += nw)
+    { const int64_t b0 = boff[r];
+      const int len = (int) (boff[r + 1] - b0 - 1);
+      const uint8_t *p = packed + poff[r];
+      uint8_t *d = bases + b0;
+      if (lane == 0)
+        { d[len] = 4;
+          if (r == 0) d[-1] = 4;
+        }
+      const int nbytes = (len + 3) >> 2;
+      for (int j = lane; j < nbytes; j += 32)
+        { const uint32_t c = p[j];
+          const int i = 4 * j;
+          d[i] = (uint8_t) (c >> 6);
+          if (i + 1 < len) d[i + 1] = (uint8_t) ((c >> 4) & 3);
+          if (i + 2 < len) d[i + 2] = (uint8_t) ((c >> 2) & 3);
+          if (i + 3 < len) d[i + 3] = (uint8_t) (c & 3);
+        }
+    }
+}
+
+DeviceBlock *upload_block_packed(const uint8_t *packed, const int64_t *poff, int64_t packed_bytes,
+                                 const int64_t *boff, const int32_t *rlen, int nreads, int tfirst,
+                                 int maxlen, int64_t totlen, int64_t sizeof_db, cudaStream_t stream)
+{ DeviceBlock *blk = new DeviceBlock();
+  blk->nreads = nreads; blk->tfirst = tfirst; blk->maxlen = maxlen; blk->totlen = totlen;
+  blk->sizeof_db = sizeof_db;
+  blk->total = boff[nreads];
+  blk->raw = dalloc<uint8_t>((size_t) blk->total + 2 * BLOCK_SLACK);
+  blk->bases = blk->raw + BLOCK_SLACK;
+  blk->boff = dalloc<int64_t>(nreads + 1);
+  blk->rlen = dalloc<int32_t>(nreads + 1);
+  uint8_t *d_packed = dalloc<uint8_t>((size_t) packed_bytes + 16);
+  int64_t *d_poff = dalloc<int64_t>(nreads + 1);
+  CUDA_CHECK(cudaMemcpyAsync(d_packed, packed, (size_t) packed_bytes, cudaMemcpyHostToDevice, stream));
+  CUDA_CHECK(cudaMemcpyAsync(d_poff, poff, sizeof(int64_t) * nreads, cudaMemcpyHostToDevice, stream));
+  CUDA_CHECK(cudaMemcpyAsync(blk->boff, boff, sizeof(int64_t) * (nreads + 1), cudaMemcpyHostToDevice, stream));
+  CUDA_CHECK(cudaMemcpyAsync(blk->rlen, rlen, sizeof(int32_t) * nreads, cudaMemcpyHostToDevice, stream));
+  if (nreads > 0)
+    { int grid = (nreads + 7) / 8;
+      if (grid > sm_count() * 16) grid = sm_count() * 16;
+      LAUNCH(k_unpack_bps, grid, 256, 0, stream, d_packed, d_poff, blk->boff, nreads, blk->bases);
+    }
+  else
+    CUDA_CHECK(cudaMemsetAsync(blk->bases - 1, 4, 1, stream));
+  blk->h_boff.assign(boff, boff + nreads + 1);
+  blk->h_rlen.assign(rlen, rlen + nreads);
+  CUDA_CHECK(cudaStreamSynchronize(stream));
+  dfree(d_packed); dfree(d_poff);
+  return blk;
+}
+
 // In-place reverse complement of every read (complement, damapper.c:417-431).  One thread per
 // base position of the first half of its read: position q of read r swaps with its mirror.
 __global__ void __launch_bounds__(256)

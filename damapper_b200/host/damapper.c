@@ -256,7 +256,7 @@ int main(int argc, char *argv[])
       damgpu_mapper *mapper;
       damgpu_report *rep;
 
-      if (dazz_load(argv[i],&bblock) != 0)
+      if (dazz_load_packed(argv[i],&bblock) != 0)       /* 2 bits per base to the device */
         Clean_Exit(1);
       for (k = 0; k < bblock.nreads; k++)
         if (bblock.rlen[k] < KMER_LEN)
@@ -273,18 +273,18 @@ int main(int argc, char *argv[])
       dazz_view(&bblock,&bview);
       if (VERBOSE)
         printf("\nBuilding index for %s\n",broot);
-      dreads = damgpu_block_upload(&bview);
+      dreads = damgpu_block_upload_packed(&bview,bblock.packed,bblock.poff,bblock.packed_bytes);
       bindex = damgpu_index_build(dreads);
       mapper = damgpu_mapper_new(dreads,bindex);
 
       for (k = 1; k <= refdb.nblocks; k++)
         { snprintf(name,sizeof(name),"%s/%s.%d.%s",refdb.pwd,aroot,k,refdb.isdam ? "dam" : "db");
-          if (dazz_load(name,&ablock) != 0)
+          if (dazz_load_packed(name,&ablock) != 0)
             Clean_Exit(1);
           dazz_view(&ablock,&aview);
           if (VERBOSE)
             printf("\nBuilding index for %s.%d\n",aroot,k);
-          dref = damgpu_block_upload(&aview);
+          dref = damgpu_block_upload_packed(&aview,ablock.packed,ablock.poff,ablock.packed_bytes);
           aindex = damgpu_index_build(dref);
           if (VERBOSE)
             printf("\nComparing %s to %s.%d\n",broot,aroot,k);
@@ -304,12 +304,12 @@ int main(int argc, char *argv[])
         }
 
       snprintf(name,sizeof(name),"%s/%s.%s",refdb.pwd,aroot,refdb.isdam ? "dam" : "db");
-      if (dazz_load(name,&ablock) != 0)
+      if (dazz_load_packed(name,&ablock) != 0)
         Clean_Exit(1);
       dazz_view(&ablock,&aview);
       if (VERBOSE)
         printf("\nFinding best matches for block %s\n",broot);
-      dref = damgpu_block_upload(&aview);
+      dref = damgpu_block_upload_packed(&aview,ablock.packed,ablock.poff,ablock.packed_bytes);
       rep  = damgpu_mapper_report(mapper,dref,&spec,mflag);
       { int nfiles = 1;
         while (2*nfiles <= NTHREADS) nfiles *= 2;

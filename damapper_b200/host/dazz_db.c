@@ -104,7 +104,7 @@ int dazz_open(const char *name, Dazz_Block *db)
   return (0);
 }
 
-int dazz_load(const char *name, Dazz_Block *db)
+static int load_block(const char *name, Dazz_Block *db, int keep_packed)
 { char  path[4096], a[2048], b[2048];
   FILE *f;
   int   ext, nfiles, nblocks = 0, cutoff = 0, all = 1, i, x;
@@ -187,10 +187,17 @@ int dazz_load(const char *name, Dazz_Block *db)
           if (recs[u].rlen > maxlen) maxlen = recs[u].rlen;
         }
     db->nreads = n; db->tfirst = tfirst; db->totlen = tot; db->maxlen = maxlen;
-    db->raw  = (uint8_t *) malloc((size_t) (tot + n + 8));
+    db->raw = db->packed = NULL; db->poff = NULL; db->packed_bytes = 0;
+    if (keep_packed)
+      { db->packed = (uint8_t *) malloc((size_t) (tot/4 + n + 8));
+        db->poff   = (int64_t *) malloc(sizeof(int64_t)*(size_t) (n+1));
+      }
+    else
+      db->raw  = (uint8_t *) malloc((size_t) (tot + n + 8));
     db->boff = (int64_t *) malloc(sizeof(int64_t)*(size_t) (n+1));
     db->rlen = (int32_t *) malloc(sizeof(int32_t)*(size_t) (n+1));
-    if (db->raw == NULL || db->boff == NULL || db->rlen == NULL)
+    if ((keep_packed ? (db->packed == NULL || db->poff == NULL) : db->raw == NULL) ||
+        db->boff == NULL || db->rlen == NULL)
       { fprintf(stderr,"damapper: Out of memory (Allocating All Sequence Reads)\n");
         return (-1);
       }
@@ -199,22 +206,30 @@ int dazz_load(const char *name, Dazz_Block *db)
       { fprintf(stderr,"damapper: Cannot open %s\n",path);
         return (-1);
       }
-    db->raw[0] = 4;
+    if (!keep_packed)
+      db->raw[0] = 4;
     n = 0;
     for (u = ufirst; u < ulast; u++)
       if ((all || (recs[u].flags & DB_BEST)) && recs[u].rlen >= cutoff)
         { int      len = recs[u].rlen, clen = (len+3) >> 2, j;
-          uint8_t *s = db->raw + 1 + o;
-          uint8_t *c = s + (len - clen);           /* read the packed bytes into the tail */
+          uint8_t *s = keep_packed ? NULL : db->raw + 1 + o;
+          uint8_t *c = keep_packed ? db->packed + db->packed_bytes
+                                   : s + (len - clen);   /* read the packed bytes into the tail */
           if (len < 0 || fseeko(bps,recs[u].boff,SEEK_SET) != 0 ||
               (clen > 0 && fread(c,1,(size_t) clen,bps) != (size_t) clen))
             { fprintf(stderr,"damapper: Read of .bps file failed\n");
               fclose(bps);
               return (-1);
             }
-          for (j = 0; j < len; j++)                /* first base in the two top bits */
-            s[j] = (uint8_t) ((c[j >> 2] >> (6 - 2*(j & 3))) & 3);
-          s[len] = 4;
+          if (keep_packed)
+            { db->poff[n] = db->packed_bytes;
+              db->packed_bytes += clen;
+            }
+          else
+            { for (j = 0; j < len; j++)            /* first base in the two top bits */
+                s[j] = (uint8_t) ((c[j >> 2] >> (6 - 2*(j & 3))) & 3);
+              s[len] = 4;
+            }
           db->boff[n] = o;
           db->rlen[n] = len;
           o += len+1;
@@ -227,8 +242,11 @@ int dazz_load(const char *name, Dazz_Block *db)
   return (0);
 }
 
+int dazz_load(const char *name, Dazz_Block *db)        { return (load_block(name,db,0)); }
+int dazz_load_packed(const char *name, Dazz_Block *db) { return (load_block(name,db,1)); }
+
 void dazz_close(Dazz_Block *db)
-{ free(db->raw); free(db->boff); free(db->rlen); free(db->root); free(db->pwd);
+{ free(db->raw); free(db->packed); free(db->poff); free(db->boff); free(db->rlen); free(db->root); free(db->pwd);
   memset(db,0,sizeof(*db));
 }
 
@@ -250,7 +268,7 @@ void dazz_complement(Dazz_Block *db)
 }
 
 void dazz_view(const Dazz_Block *db, damgpu_block *v)
-{ v->bases = db->raw + 1;
+{ v->bases = (db->raw != NULL) ? db->raw + 1 : NULL;
   v->boff = db->boff;
   v->rlen = db->rlen;
   v->nreads = db->nreads;

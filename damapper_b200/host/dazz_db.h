@@ -19,7 +19,10 @@ typedef struct
     /* loaded (trimmed) block */
     int      nreads, tfirst, maxlen;
     int64_t  totlen;
-    uint8_t *raw;         /* allocation; bases = raw+1, raw[0] = 4 */
+    uint8_t *raw;         /* allocation; bases = raw+1, raw[0] = 4 (NULL when loaded packed) */
+    uint8_t *packed;      /* the reads as .bps holds them, 2 bits per base (packed loads only) */
+    int64_t *poff;        /* nreads byte offsets into packed */
+    int64_t  packed_bytes;
     int64_t *boff;        /* nreads+1 */
     int32_t *rlen;
     int64_t  path_len;    /* strlen(db->path) of the reference, enters sizeof_DB (DB.c:1050) */
@@ -29,6 +32,8 @@ typedef struct
 int  dazz_open(const char *name, Dazz_Block *db);
 /* Loads block `part` (0 = all, or the .N suffix given in `name`) with all reads in memory. */
 int  dazz_load(const char *name, Dazz_Block *db);
+/* The same, but the reads stay 2-bit packed (db->packed/poff): the device expands them. */
+int  dazz_load_packed(const char *name, Dazz_Block *db);
 void dazz_close(Dazz_Block *db);
 /* In-place reverse complement of every read (complement_DB, damapper.c:433-469). */
 void dazz_complement(Dazz_Block *db);

@@ -98,6 +98,13 @@ void  damgpu_Reporter(const char *aname, const damgpu_block *ablock, const char 
 
 /* ---- layer 2: resident handles -------------------------------------------------------- */
 damgpu_dblock *damgpu_block_upload(const damgpu_block *block);
+/* The same block from the .bps image as it is on disk: read i is
+ * rlen[i] bases packed four per byte, first base in the two top bits (Compress_Read /
+ * Uncompress_Read, DB.c:319-363), starting at packed[poff[i]]; the Load_All_Reads image
+ * (DB.c:1389-1441) is built on the device, so a quarter of the bytes cross PCIe and the host
+ * never expands a base.  block->bases is ignored (may be NULL), the other fields are as above. */
+damgpu_dblock *damgpu_block_upload_packed(const damgpu_block *block, const uint8_t *packed,
+                                          const int64_t *poff, int64_t packed_bytes);
 void           damgpu_block_free(damgpu_dblock *blk);
 /* complement_DB(block, inplace=1), damapper.c:433-469, on the device */
 void           damgpu_block_complement(damgpu_dblock *blk);

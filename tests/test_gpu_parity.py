@@ -254,6 +254,33 @@ def test_full_size_properties(api):
     assert out["stats"]["overflow_jobs"] == 0 or out["stats"]["overflow_jobs"] < 50
 
 
+def test_packed_bps_upload_decodes_on_the_device(api, oracle_mod):
+    """the .bps image (2 bits per base) expanded on the device gives the
+    Load_All_Reads image byte for byte, for ragged read lengths (all residues mod 4), and the
+    index built from it is the index of the plain upload."""
+    rng = np.random.default_rng(77)
+    lens = np.array([20, 21, 22, 23, 24, 57, 1001, 4099, 10000, 33], dtype=np.int32)
+    bases = rng.integers(0, 4, size=int(lens.sum()), dtype=np.uint8)
+    from damapper_b200 import dazzdb
+    rd = dazzdb.load_block((bases, lens))
+    hb = api.HostBlock(*rd)
+    api.set_filter_params(20, 0, 4)
+    api.set_options()
+    plain, packed = api.DeviceBlock(hb), api.DeviceBlock(hb, packed=True)
+    a, b = plain.download_bases(), packed.download_bases()
+    n1 = int(hb.boff[-1]) + 1                            # leading 4 + every read and its terminator
+    bad = np.nonzero(a[:n1] != b[:n1])[0]
+    assert bad.size == 0, ("packed != plain", bad[:8], a[bad[:8]], b[bad[:8]])
+    assert b[:n1].tobytes() == hb.bases[:n1].tobytes()
+    ia, ib = api.Index(plain), api.Index(packed)
+    assert ia.download().tobytes() == ib.download().tobytes()
+    ia.free(); ib.free(); plain.free(); packed.free()
+    empty = api.HostBlock(np.array([4], dtype=np.uint8), np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int32))
+    e = api.DeviceBlock(empty, packed=True)
+    assert e.download_bases().tobytes() == empty.bases.tobytes()
+    e.free()
+
+
 def test_full_size_c2_matches_oracle(api, oracle_mod):
     """BASELINE config 2 at FULL size (4.6 Mbp + 13.8 k reads, the bench workload): every M and R
     record and the -p track bit for bit against the oracle (about half a minute of one host core)."""
