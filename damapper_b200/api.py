@@ -23,7 +23,8 @@ CAND_DT = np.dtype([(n, "<i4") for n in ("read", "score", "length", "bread", "co
 class CBlock(C.Structure):
     _fields_ = [("bases", C.c_void_p), ("boff", C.c_void_p), ("rlen", C.c_void_p),
                 ("nreads", C.c_int32), ("tfirst", C.c_int32), ("maxlen", C.c_int32),
-                ("totlen", C.c_int64), ("sizeof_db", C.c_int64)]
+                ("totlen", C.c_int64), ("sizeof_db", C.c_int64),
+                ("mask_off", C.c_void_p), ("mask_pts", C.c_void_p)]
 
 
 class COptions(C.Structure):
@@ -122,7 +123,7 @@ class HostBlock:
     """Host image of a loaded DB block (what Load_All_Reads leaves in DAZZ_DB)."""
 
     def __init__(self, bases: np.ndarray, boff: np.ndarray, rlen: np.ndarray, tfirst: int = 0,
-                 path_len: int = 16):
+                 path_len: int = 16, mask=None):
         self.bases = np.ascontiguousarray(bases, dtype=np.uint8)     # leading 4 at index 0
         self.boff = np.ascontiguousarray(boff, dtype=np.int64)
         self.rlen = np.ascontiguousarray(rlen, dtype=np.int32)
@@ -132,8 +133,14 @@ class HostBlock:
         self.totlen = int(self.rlen.sum())
         self.sizeof_db = (112 + 40 * (self.nreads + 2) + path_len + 1
                           + (self.totlen + self.nreads + 4))       # sizeof_DB, DB.c:1044-1051
+        self.mask_off = self.mask_pts = None
+        if mask is not None:                                # (offsets in ints [nreads+1], points)
+            self.mask_off = np.ascontiguousarray(mask[0], dtype=np.int64)
+            self.mask_pts = np.ascontiguousarray(np.concatenate([mask[1], [0]]), dtype=np.int32)
         self.c = CBlock(self.bases.ctypes.data + 1, self.boff.ctypes.data, self.rlen.ctypes.data,
-                        self.nreads, tfirst, self.maxlen, self.totlen, self.sizeof_db)
+                        self.nreads, tfirst, self.maxlen, self.totlen, self.sizeof_db,
+                        self.mask_off.ctypes.data if mask is not None else None,
+                        self.mask_pts.ctypes.data if mask is not None else None)
 
 
 def set_filter_params(kmer: int = 20, suppress: int = 0, nthreads: int = 4) -> int:

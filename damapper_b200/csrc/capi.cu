@@ -112,8 +112,10 @@ static void need_gpu()
 }
 
 static DeviceBlock *upload(const damgpu_block *b)
-{ return upload_block(b->bases, b->boff, b->rlen, b->nreads, b->tfirst, b->maxlen, b->totlen,
-                      b->sizeof_db, 0);
+{ DeviceBlock *blk = upload_block(b->bases, b->boff, b->rlen, b->nreads, b->tfirst, b->maxlen,
+                                  b->totlen, b->sizeof_db, 0);
+  set_block_mask(blk, b->mask_off, b->mask_pts, 0);
+  return blk;
 }
 
 }  // namespace damgpu
@@ -192,9 +194,10 @@ damgpu_dblock *damgpu_block_upload_packed(const damgpu_block *b, const uint8_t *
 { need_gpu();
   if (b->nreads > 0 && (packed == nullptr || poff == nullptr))
     fatal("damgpu_block_upload_packed: no packed image");
-  return reinterpret_cast<damgpu_dblock *>(
-      upload_block_packed(packed, poff, packed_bytes, b->boff, b->rlen, b->nreads, b->tfirst,
-                          b->maxlen, b->totlen, b->sizeof_db, 0));
+  DeviceBlock *blk = upload_block_packed(packed, poff, packed_bytes, b->boff, b->rlen, b->nreads,
+                                         b->tfirst, b->maxlen, b->totlen, b->sizeof_db, 0);
+  set_block_mask(blk, b->mask_off, b->mask_pts, 0);
+  return reinterpret_cast<damgpu_dblock *>(blk);
 }
 
 void damgpu_block_free(damgpu_dblock *blk) { free_block(reinterpret_cast<DeviceBlock *>(blk)); }

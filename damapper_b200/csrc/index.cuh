@@ -14,6 +14,9 @@ struct DeviceBlock
   uint8_t *bases = nullptr;     // raw+BLOCK_SLACK, 16-byte aligned
   int64_t *boff = nullptr;      // nreads+1
   int32_t *rlen = nullptr;
+  int64_t *mask_off = nullptr;  // -m: merged mask track (nreads+1 offsets into mask_pts), or null
+  int32_t *mask_pts = nullptr;  //     interval end points, pairs [begin, end)
+  int64_t  nmask = 0;           //     number of points
   int      nreads = 0, tfirst = 0, maxlen = 0;
   int64_t  totlen = 0, total = 0, sizeof_db = 0;
   std::vector<int64_t> h_boff;
@@ -34,6 +37,9 @@ struct KmerIndex
 DeviceBlock *upload_block(const uint8_t *bases, const int64_t *boff, const int32_t *rlen,
                           int nreads, int tfirst, int maxlen, int64_t totlen, int64_t sizeof_db,
                           cudaStream_t stream);
+// attach the block's merged mask track (host arrays; no-op when mask_off is null)
+void         set_block_mask(DeviceBlock *blk, const int64_t *mask_off, const int32_t *mask_pts,
+                            cudaStream_t stream);
 // the same block from its .bps image (2 bits per base), expanded on the device
 DeviceBlock *upload_block_packed(const uint8_t *packed, const int64_t *poff, int64_t packed_bytes,
                                  const int64_t *boff, const int32_t *rlen, int nreads, int tfirst,

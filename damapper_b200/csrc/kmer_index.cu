@@ -20,7 +20,8 @@ constexpr int EX_MAXSPAN = 512;                       // read starts cached per 
 // in the most significant bits, so the code of a k-mer is a funnel shift of two words.
 __global__ void __launch_bounds__(EX_THREADS)
 k_extract(const uint8_t *__restrict__ bases, const int64_t *__restrict__ boff, int nreads,
-          int64_t total, int K, int npass, KmerPos *__restrict__ list, uint32_t *hist)
+          int64_t total, int K, int npass, KmerPos *__restrict__ list, uint32_t *hist,
+          const int64_t *__restrict__ mask_off, const int32_t *__restrict__ mask_pts)
 { // window = [t0-32, t0+EX_TILE): 32 bases of left context (K <= 32)
   __shared__ uint64_t s_pack[EX_TILE / 32 + 2];
   __shared__ int64_t  s_boff[EX_MAXSPAN + 2];
@@ -126,6 +127,20 @@ k_extract(const uint8_t *__restrict__ bases, const int64_t *__restrict__ boff, i
           const int64_t g = q + 1 - (int64_t) (r + 1) * K;
           KmerPos kp;
           kp.code = code; kp.rpos = rpos; kp.read = r;
+          if (mask_off != nullptr)                    // -m, map.c:481-543: the k-mer must lie inside
+            { const int64_t mb = mask_off[r], mf = mask_off[r + 1];     // an unmasked segment
+              int64_t lo = 0, hi = (mf - mb) >> 1;    // first interval whose begin is > rpos
+              while (lo < hi)
+                { const int64_t mid = (lo + hi) >> 1;
+                  if (mask_pts[mb + 2 * mid] > rpos) hi = mid; else lo = mid + 1;
+                }
+              const int p = (lo == 0) ? 0 : mask_pts[mb + 2 * lo - 1];  // end of the interval before
+              if (rpos - (K - 1) < p)
+                { kp.code = ~0ull; kp.rpos = -1; kp.read = -1;          // dropped by the compaction
+                  *reinterpret_cast<uint4 *>(list + g) = *reinterpret_cast<uint4 *>(&kp);
+                  continue;
+                }
+            }
           *reinterpret_cast<uint4 *>(list + g) = *reinterpret_cast<uint4 *>(&kp);
           for (int p = 0; p < npass; p++)
             atomicAdd(&s_hist[p * 256 + ((code >> (8 * p)) & 0xff)], 1u);
@@ -163,6 +178,12 @@ __global__ void k_suppress_flags(const KmerPos *__restrict__ list, int64_t n, in
       if (list[mid].code == c) lo = mid; else hi = mid - 1;
     }
   keep[i] = (lo - left + 1 < t) ? 1u : 0u;
+}
+
+// -m: keep[i] = 1 iff slot i holds a real k-mer (masked slots carry read == -1)
+__global__ void k_mask_flags(const KmerPos *__restrict__ list, int64_t n, uint32_t *__restrict__ keep)
+{ int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keep[i] = (list[i].read != -1) ? 1u : 0u;
 }
 
 // block-wise exclusive scan of keep flags (three-kernel scan; -t is off the default path)
@@ -315,6 +336,39 @@ DeviceBlock *upload_block_packed(const uint8_t *packed, const int64_t *poff, int
   return blk;
 }
 
+void set_block_mask(DeviceBlock *blk, const int64_t *mask_off, const int32_t *mask_pts,
+                    cudaStream_t stream)
+{ if (mask_off == nullptr)
+    return;
+  const int n = blk->nreads;
+  blk->nmask = mask_off[n];
+  blk->mask_off = dalloc<int64_t>((size_t) n + 1);
+  blk->mask_pts = dalloc<int32_t>((size_t) blk->nmask + 1);
+  CUDA_CHECK(cudaMemcpyAsync(blk->mask_off, mask_off, sizeof(int64_t) * ((size_t) n + 1),
+                             cudaMemcpyHostToDevice, stream));
+  if (blk->nmask > 0)
+    CUDA_CHECK(cudaMemcpyAsync(blk->mask_pts, mask_pts, sizeof(int32_t) * (size_t) blk->nmask,
+                               cudaMemcpyHostToDevice, stream));
+  CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+// Mask intervals of a complemented block (complement_DB, damapper.c:471-522): the point list of
+// every read is reversed and each point x becomes rlen - x.  One thread per read.
+__global__ void k_mirror_mask(const int64_t *__restrict__ mask_off, int32_t *mask_pts,
+                              const int32_t *__restrict__ rlen, int nreads)
+{ const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nreads) return;
+  const int len = rlen[r];
+  int64_t k = mask_off[r], j = mask_off[r + 1] - 1;
+  while (k < j)
+    { const int x = mask_pts[j];
+      mask_pts[j--] = len - mask_pts[k];
+      mask_pts[k++] = len - x;
+    }
+  if (k == j)
+    mask_pts[k] = len - mask_pts[k];
+}
+
 // In-place reverse complement of every read (complement, damapper.c:417-431).  One thread per
 // base position of the first half of its read: position q of read r swaps with its mirror.
 __global__ void __launch_bounds__(256)
@@ -384,11 +438,15 @@ void complement_block(DeviceBlock *blk, cudaStream_t stream)
   int64_t nb = (blk->total + 255) / 256;
   int grid = nb < (int64_t) sm_count() * 16 ? (int) nb : sm_count() * 16;
   LAUNCH(k_complement, grid, 256, 0, stream, blk->bases, blk->boff, blk->nreads, blk->total);
+  if (blk->mask_off != nullptr)
+    LAUNCH(k_mirror_mask, (blk->nreads + 255) / 256, 256, 0, stream, blk->mask_off, blk->mask_pts,
+           blk->rlen, blk->nreads);
 }
 
 void free_block(DeviceBlock *blk)
 { if (blk == nullptr) return;
   dfree(blk->raw); dfree(blk->boff); dfree(blk->rlen);
+  dfree(blk->mask_off); dfree(blk->mask_pts);
   delete blk;
 }
 
@@ -426,10 +484,24 @@ KmerIndex *sort_kmers(const DeviceBlock *blk, int K, int suppress, cudaStream_t 
       cudaEventRecord(e0, stream);
     }
   LAUNCH(k_extract, grid, EX_THREADS, 0, stream, blk->bases, blk->boff, nreads, blk->total, K,
-         npass, a, hist);
+         npass, a, hist, blk->mask_off, blk->mask_pts);
+  uint32_t nlist = n;                                  // records that go into the sort
+  if (blk->mask_off != nullptr)                        // -m: squeeze out the masked slots, in order
+    { uint32_t *keep = dalloc<uint32_t>(n);
+      int nb = (int) ((n + 2047) / 2048);
+      uint32_t *bsum = dalloc<uint32_t>(nb + 1);
+      LAUNCH(k_mask_flags, (n + 255) / 256, 256, 0, stream, a, (int64_t) n, keep);
+      LAUNCH(k_scan_blocks, nb, 256, 0, stream, keep, (int64_t) n, bsum);
+      LAUNCH(k_scan_bsum, 1, 1024, 0, stream, bsum, nb, bsum + nb);
+      LAUNCH(k_compact, nb, 256, 0, stream, a, keep, (int64_t) n, bsum, b);
+      CUDA_CHECK(cudaMemcpyAsync(&nlist, bsum + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+      CUDA_CHECK(cudaStreamSynchronize(stream));
+      dfree(keep); dfree(bsum);
+      KmerPos *t = a; a = b; b = t;
+    }
   TRACE("sort_kmers: alloc+extract");
   if (g_time_kernels) cudaEventRecord(e1, stream);
-  KmerPos *rez = (KmerPos *) radix_sort16(a, b, n, bytes, npass, hist, stream);
+  KmerPos *rez = (KmerPos *) radix_sort16(a, b, nlist, bytes, npass, hist, stream);
   if (g_time_kernels)
     { cudaEventRecord(e2, stream);
       cudaEventSynchronize(e2);
@@ -443,9 +515,10 @@ KmerIndex *sort_kmers(const DeviceBlock *blk, int K, int suppress, cudaStream_t 
   KmerPos *other = (rez == a) ? b : a;
   dfree(hist);
 
-  uint32_t kept = n;
-  if (suppress > 0)                                    // map.c:726-770
-    { uint32_t *keep = dalloc<uint32_t>(n);
+  uint32_t kept = nlist;
+  if (suppress > 0 && nlist > 0)                       // map.c:726-770
+    { const uint32_t n = nlist;
+      uint32_t *keep = dalloc<uint32_t>(n);
       int nb = (int) ((n + 2047) / 2048);
       uint32_t *bsum = dalloc<uint32_t>(nb + 1);
       LAUNCH(k_suppress_flags, (n + 255) / 256, 256, 0, stream, rez, (int64_t) n, suppress, keep);

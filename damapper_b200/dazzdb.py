@@ -118,3 +118,36 @@ def load_block(seqs) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
 def revcomp_contigs(contigs):
     """complement_DB (reference damapper.c:433-525): reverse-complement every contig in place."""
     return [(3 - c[::-1]).astype(np.uint8) for c in contigs]
+
+
+def random_masks(rlen, seed: int = 1, max_intervals: int = 3, max_len: int = 400):
+    """A merged mask track for reads of lengths `rlen`: (offsets [n+1] counting ints, points) with
+    sorted, disjoint [begin, end) intervals per read, some touching the read ends (the form
+    block->tracks has after damapper.c:381-399)."""
+    rng = np.random.default_rng(seed)
+    off, pts = [0], []
+    for n in np.asarray(rlen, dtype=np.int64):
+        k = int(rng.integers(0, max_intervals + 1))
+        cuts = np.sort(rng.choice(np.arange(0, int(n) + 1), size=min(2 * k, int(n) + 1), replace=False))
+        iv = []
+        for j in range(0, cuts.size - 1, 2):
+            b, e = int(cuts[j]), int(min(cuts[j + 1], cuts[j] + max_len))
+            if e > b:
+                iv += [b, e]
+        if k and rng.random() < 0.2 and iv:
+            iv[0] = 0                                   # starts at the first base
+        if k and rng.random() < 0.2 and iv:
+            iv[-1] = int(n)                             # ends at the last base
+        pts += iv
+        off.append(len(pts))
+    return np.asarray(off, dtype=np.int64), np.asarray(pts, dtype=np.int32)
+
+
+def mirror_masks(off, pts, rlen):
+    """Mask track of the complemented block (complement_DB, reference damapper.c:471-522): per read
+    the point list is reversed and every point x becomes rlen - x."""
+    out = np.array(pts, dtype=np.int32, copy=True)
+    for i, n in enumerate(np.asarray(rlen, dtype=np.int64)):
+        b, e = int(off[i]), int(off[i + 1])
+        out[b:e] = (int(n) - np.asarray(pts[b:e], dtype=np.int64))[::-1]
+    return np.asarray(off, dtype=np.int64), out

@@ -275,6 +275,7 @@ void dazz_view(const Dazz_Block *db, damgpu_block *v)
   v->tfirst = db->tfirst;
   v->maxlen = db->maxlen;
   v->totlen = db->totlen;
+  v->mask_off = NULL; v->mask_pts = NULL;
   /* sizeof_DB, DB.c:1044-1051: sizeof(DAZZ_DB)=112, sizeof(DAZZ_READ)=40 */
   v->sizeof_db = 112 + 40*((int64_t) db->nreads+2) + db->path_len + 1 + (db->totlen + db->nreads + 4);
 }

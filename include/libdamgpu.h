@@ -42,6 +42,12 @@ typedef struct {
   int32_t  maxlen;          /* DAZZ_DB.maxlen */
   int64_t  totlen;          /* DAZZ_DB.totlen */
   int64_t  sizeof_db;       /* sizeof_DB(block), DB.c:1044 -- enters the k-mer hit cap */
+  /* -m: the single merged mask track of the block (block->tracks after damapper.c:381-399): read i
+   * is masked over [mask_pts[j], mask_pts[j+1]) for j = mask_off[i], mask_off[i]+2, .. below
+   * mask_off[i+1] (offsets count ints, as after the division at damapper.c:385-387); k-mers that
+   * touch a masked base are not indexed (tuple_thread, map.c:481-543).  NULL = no mask. */
+  const int64_t *mask_off;  /* nreads+1 entries, or NULL */
+  const int32_t *mask_pts;
 } damgpu_block;
 
 /* The globals map.h:16-23 declares extern and damapper.c:58-65 defines. */

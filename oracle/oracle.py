@@ -23,7 +23,8 @@ CAND_DT = np.dtype([(n, "<i4") for n in ("read", "score", "length", "bread", "co
 class Block(C.Structure):
     _fields_ = [("bases", C.c_void_p), ("boff", C.c_void_p), ("rlen", C.c_void_p),
                 ("nreads", C.c_int32), ("tfirst", C.c_int32), ("maxlen", C.c_int32),
-                ("totlen", C.c_int64), ("sizeof_db", C.c_int64)]
+                ("totlen", C.c_int64), ("sizeof_db", C.c_int64),
+                ("mask_off", C.c_void_p), ("mask_pts", C.c_void_p)]
 
 
 class Params(C.Structure):
@@ -86,7 +87,7 @@ class HostBlock:
     """A loaded DB block (Load_All_Reads image) kept alive for ctypes calls."""
 
     def __init__(self, bases: np.ndarray, boff: np.ndarray, rlen: np.ndarray, tfirst: int = 0,
-                 path_len: int = 16):
+                 path_len: int = 16, mask=None):
         # `bases` carries the leading 4 at index 0 (damapper_b200.dazzdb.load_block)
         self.bases = np.ascontiguousarray(bases, dtype=np.uint8)
         self.boff = np.ascontiguousarray(boff, dtype=np.int64)
@@ -97,8 +98,14 @@ class HostBlock:
         self.totlen = int(self.rlen.sum())
         # sizeof_DB (DB.c:1044-1051): sizeof(DAZZ_DB)=112, sizeof(DAZZ_READ)=40
         self.sizeof_db = 112 + 40 * (self.nreads + 2) + path_len + 1 + (self.totlen + self.nreads + 4)
+        self.mask_off = self.mask_pts = None
+        if mask is not None:
+            self.mask_off = np.ascontiguousarray(mask[0], dtype=np.int64)
+            self.mask_pts = np.ascontiguousarray(np.concatenate([mask[1], [0]]), dtype=np.int32)
         self.c = Block(self.bases.ctypes.data + 1, self.boff.ctypes.data, self.rlen.ctypes.data,
-                       self.nreads, tfirst, self.maxlen, self.totlen, self.sizeof_db)
+                       self.nreads, tfirst, self.maxlen, self.totlen, self.sizeof_db,
+                       self.mask_off.ctypes.data if mask is not None else None,
+                       self.mask_pts.ctypes.data if mask is not None else None)
 
 
 def sort_kmers(blk: HostBlock, kmer: int, suppress: int = 0) -> np.ndarray:

@@ -55,24 +55,36 @@ orc_kmer *orc_sort_kmers(const orc_block *blk, int kmer, int suppress, int *len)
   n = 0;
   for (i = 0; i < nreads; i++)
     { const uint8_t *s = blk->bases + blk->boff[i];
-      int      q = blk->rlen[i], p = 0, x;
-      uint64_t c = 0;
-      if (p + kmer <= q)
-        { for (x = 1; x < kmer; x++)
-            c = (c << 2) | s[p++];
-          while (p < q)
-            { c = ((c << 2) | s[p]) & kmask;
-              src[n].read = i;
-              src[n].rpos = p++;
-              src[n].code = c;
-              n += 1;
+      int64_t  b = 0, f = 0, a;
+      if (blk->mask_off != NULL)                     /* masked branch, map.c:481-543 */
+        { b = blk->mask_off[i]; f = blk->mask_off[i+1]; }
+      for (a = b; a <= f; a += 2)                    /* unmasked segment [p,q) before interval a */
+        { int      p = (a == b) ? 0 : blk->mask_pts[a-1];
+          int      q = (a == f) ? blk->rlen[i] : blk->mask_pts[a];
+          int      x;
+          uint64_t c = 0;
+          if (p + kmer <= q)
+            { for (x = 1; x < kmer; x++)
+                c = (c << 2) | s[p++];
+              while (p < q)
+                { c = ((c << 2) | s[p]) & kmask;
+                  src[n].read = i;
+                  src[n].rpos = p++;
+                  src[n].code = c;
+                  n += 1;
+                }
             }
         }
     }
   /* reads shorter than k contribute a negative count to `kmers` in the reference; it rejects
-     such blocks up front (damapper.c:403-410), so n == kmers here. */
-  if (n != kmers)
+     such blocks up front (damapper.c:403-410), so n == kmers here.  With a mask the reference pads
+     the missing slots with ~0 records that sort to the end and are cut off (map.c:524-532,
+     :706-724): the list is the n real k-mers. */
+  if (blk->mask_off == NULL && n != kmers)
     { fprintf(stderr,"oracle: block holds reads shorter than k\n"); exit (1); }
+  kmers = (int) n;
+  if (kmers == 0)
+    { free(src); free(trg); return (NULL); }
 
   for (i = 0; i < 16; i++)
     mersort[i] = 0;

@@ -254,6 +254,42 @@ def test_full_size_properties(api):
     assert out["stats"]["overflow_jobs"] == 0 or out["stats"]["overflow_jobs"] < 50
 
 
+@pytest.mark.parametrize("cfg,scale,seed,kw", [
+    ("C1", 0.1, 61, dict(do_b=1)),
+    ("C3", 0.004, 62, dict(profile=1, best_tie=0.9)),
+])
+def test_mask_tracks(api, oracle_mod, cfg, scale, seed, kw):
+    """-m: k-mers touching a masked base are not indexed (tuple_thread,
+    map.c:481-543); the mask of the complemented reference block is mirrored (damapper.c:471-522).
+    Index, complemented index and the whole pipeline against the oracle."""
+    from damapper_b200 import dazzdb
+    contigs, rb, rl, rd, rf, rc = make_case(cfg, scale, seed)
+    freq = base_freq(contigs)
+    mr = dazzdb.random_masks(rd[2], seed=seed, max_intervals=3, max_len=600)
+    mg = dazzdb.random_masks(rf[2], seed=seed + 1, max_intervals=40, max_len=2000)
+    mc = dazzdb.mirror_masks(mg[0], mg[1], rf[2])
+    O, A = oracle_mod.HostBlock, api.HostBlock
+    api.set_filter_params(20, 0, 4)
+    api.set_options()
+    # index of the masked reads block, and of the masked reference in both orientations
+    dr = api.DeviceBlock(A(*rd, mask=mr))
+    ir = api.Index(dr)
+    oi = oracle_mod.sort_kmers(O(*rd, mask=mr), 20, 0)
+    assert ir.download().tobytes() == oi.tobytes()
+    assert len(ir) < int(rd[1][-1]) - 20 * len(rd[2])          # something was masked
+    dg = api.DeviceBlock(A(*rf, mask=mg))
+    ig = api.Index(dg)
+    assert ig.download().tobytes() == oracle_mod.sort_kmers(O(*rf, mask=mg), 20, 0).tobytes()
+    ig.free(); dg.complement(); ig = api.Index(dg)
+    assert ig.download().tobytes() == oracle_mod.sort_kmers(O(*rc, mask=mc), 20, 0).tobytes()
+    ig.free(); dg.free(); ir.free(); dr.free()
+    # whole pipeline (the Reporter sees the unmasked whole reference, damapper.c:870)
+    o = oracle_mod.map_block(O(*rd, mask=mr), [(O(*rf, mask=mg), O(*rc, mask=mc))], O(*rf), freq=freq, **kw)
+    g = api.map_block(A(*rd, mask=mr), [A(*rf, mask=mg)], A(*rf), freq=freq, **kw)
+    assert g["anrec"] == o["anrec"] > 0
+    assert g["a"] == o["a"] and g["b"] == o["b"] and g["prof"] == o["prof"]
+
+
 def test_packed_bps_upload_decodes_on_the_device(api, oracle_mod):
     """the .bps image (2 bits per base) expanded on the device gives the
     Load_All_Reads image byte for byte, for ragged read lengths (all residues mod 4), and the
