@@ -151,3 +151,42 @@ def mirror_masks(off, pts, rlen):
         b, e = int(off[i]), int(off[i + 1])
         out[b:e] = (int(n) - np.asarray(pts[b:e], dtype=np.int64))[::-1]
     return np.asarray(off, dtype=np.int64), out
+
+
+def write_mask_track(stub: str, name: str, off, pts) -> None:
+    """Write mask track `name` of the DB whose stub is `stub` (whole-DB track over the untrimmed
+    reads): .<root>.<name>.anno = int32 nreads, int32 0, int64 byte offsets [nreads+1];
+    .<root>.<name>.data = int32 interval end points (reference DB.c:1649-1702,1804-1990)."""
+    d, base = os.path.split(stub)
+    root = base
+    for ext in (".dam", ".db"):
+        if root.endswith(ext):
+            root = root[: -len(ext)]
+    off = np.asarray(off, dtype=np.int64)
+    with open(os.path.join(d or ".", ".%s.%s.anno" % (root, name)), "wb") as f:
+        f.write(np.array([off.size - 1, 0], dtype=np.int32).tobytes())
+        f.write((off * 4).astype(np.int64).tobytes())
+    with open(os.path.join(d or ".", ".%s.%s.data" % (root, name)), "wb") as f:
+        f.write(np.asarray(pts, dtype=np.int32).tobytes())
+
+
+def union_masks(a, b):
+    """Union of two mask tracks (offsets, points) read by read, as sorted disjoint intervals
+    (what merge_tracks, reference damapper.c:253-343, yields up to zero-length gaps)."""
+    off, pts = [0], []
+    for i in range(len(a[0]) - 1):
+        iv = [tuple(x) for x in np.asarray(a[1][a[0][i]:a[0][i + 1]]).reshape(-1, 2)]
+        iv += [tuple(x) for x in np.asarray(b[1][b[0][i]:b[0][i + 1]]).reshape(-1, 2)]
+        iv.sort()
+        cur = None
+        for s0, e0 in iv:
+            if cur is not None and s0 <= cur[1]:
+                cur[1] = max(cur[1], e0)
+            else:
+                if cur is not None:
+                    pts += cur
+                cur = [int(s0), int(e0)]
+        if cur is not None:
+            pts += cur
+        off.append(len(pts))
+    return np.asarray(off, dtype=np.int64), np.asarray(pts, dtype=np.int32)

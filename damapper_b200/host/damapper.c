@@ -85,6 +85,8 @@ int main(int argc, char *argv[])
   double AVE_ERROR = .85, BEST_TIE = 1.0;
   uint64_t MEM_PHYSICAL, MEM_LIMIT;
   int    mflag, i, j, k;
+  char  *MASK[256];                                       /* -m tracks (damapper.c:575-637) */
+  int    MSTAT[256];
   DIR   *dirp;
   Dazz_Block refdb, ablock, bblock;
   damgpu_options opts;
@@ -129,7 +131,11 @@ int main(int argc, char *argv[])
             }
           break;
         case 'm':
-          MTOP += 1;
+          if (MTOP >= 256)
+            { fprintf(stderr,"%s: too many -m tracks\n",Prog_Name);
+              exit (1);
+            }
+          MASK[MTOP++] = argv[i]+2;
           break;
         case 'n':
           BEST_TIE = arg_real(argv[i]);
@@ -201,11 +207,8 @@ int main(int argc, char *argv[])
     { fprintf(stderr,"%s: Cannot specify both N and p flags together\n",Prog_Name);
       exit (1);
     }
-  if (MTOP > 0)
-    { fprintf(stderr,"%s: -m mask tracks are not supported by the GPU core yet; refusing to"
-                     " ignore the mask\n",Prog_Name);
-      exit (1);
-    }
+  for (j = 0; j < MTOP; j++)                              /* damapper.c:727-728 */
+    MSTAT[j] = 0;
 
   /* reference: stub, block count, base frequencies (damapper.c:734-797) */
   if (dazz_open(argv[1],&refdb) != 0)
@@ -258,6 +261,11 @@ int main(int argc, char *argv[])
 
       if (dazz_load_packed(argv[i],&bblock) != 0)       /* 2 bits per base to the device */
         Clean_Exit(1);
+      for (j = 0; j < MTOP; j++)                        /* read_DB, damapper.c:352-399 */
+        { int st = dazz_add_mask(&bblock,MASK[j],Prog_Name);
+          if (st < 0) Clean_Exit(1);
+          if (st > 0) MSTAT[j] = 1;
+        }
       for (k = 0; k < bblock.nreads; k++)
         if (bblock.rlen[k] < KMER_LEN)
           { fprintf(stderr,"%s: Block %s contains reads < %dbp long !  Run DBsplit -x%d\n",
@@ -281,6 +289,11 @@ int main(int argc, char *argv[])
         { snprintf(name,sizeof(name),"%s/%s.%d.%s",refdb.pwd,aroot,k,refdb.isdam ? "dam" : "db");
           if (dazz_load_packed(name,&ablock) != 0)
             Clean_Exit(1);
+          for (j = 0; j < MTOP; j++)
+            { int st = dazz_add_mask(&ablock,MASK[j],Prog_Name);
+              if (st < 0) Clean_Exit(1);
+              if (st > 0) MSTAT[j] = 1;
+            }
           dazz_view(&ablock,&aview);
           if (VERBOSE)
             printf("\nBuilding index for %s.%d\n",aroot,k);
@@ -350,6 +363,10 @@ int main(int argc, char *argv[])
         }
       free(broot);
     }
+
+  for (j = 0; j < MTOP; j++)                              /* damapper.c:916-918 */
+    if (MSTAT[j] == 0)
+      printf("%s: Warning: Track %s given but never used.\n",Prog_Name,MASK[j]);
 
   Clean_Exit(0);
   return (0);

@@ -187,6 +187,11 @@ static int load_block(const char *name, Dazz_Block *db, int keep_packed)
           if (recs[u].rlen > maxlen) maxlen = recs[u].rlen;
         }
     db->nreads = n; db->tfirst = tfirst; db->totlen = tot; db->maxlen = maxlen;
+    db->ufirst = ufirst; db->ulast = ulast; db->db_ureads = h.ureads; db->db_treads = h.treads;
+    db->kept = (uint8_t *) malloc((size_t) (ulast-ufirst) + 1);
+    for (u = ufirst; u < ulast; u++)
+      db->kept[u-ufirst] = (uint8_t) ((all || (recs[u].flags & DB_BEST)) && recs[u].rlen >= cutoff);
+    db->mask_off = NULL; db->mask_pts = NULL;
     db->raw = db->packed = NULL; db->poff = NULL; db->packed_bytes = 0;
     if (keep_packed)
       { db->packed = (uint8_t *) malloc((size_t) (tot/4 + n + 8));
@@ -246,7 +251,8 @@ int dazz_load(const char *name, Dazz_Block *db)        { return (load_block(name
 int dazz_load_packed(const char *name, Dazz_Block *db) { return (load_block(name,db,1)); }
 
 void dazz_close(Dazz_Block *db)
-{ free(db->raw); free(db->packed); free(db->poff); free(db->boff); free(db->rlen); free(db->root); free(db->pwd);
+{ free(db->kept); free(db->mask_off); free(db->mask_pts);
+  free(db->raw); free(db->packed); free(db->poff); free(db->boff); free(db->rlen); free(db->root); free(db->pwd);
   memset(db,0,sizeof(*db));
 }
 
@@ -275,7 +281,123 @@ void dazz_view(const Dazz_Block *db, damgpu_block *v)
   v->tfirst = db->tfirst;
   v->maxlen = db->maxlen;
   v->totlen = db->totlen;
-  v->mask_off = NULL; v->mask_pts = NULL;
+  v->mask_off = db->mask_off; v->mask_pts = db->mask_pts;
   /* sizeof_DB, DB.c:1044-1051: sizeof(DAZZ_DB)=112, sizeof(DAZZ_READ)=40 */
   v->sizeof_db = 112 + 40*((int64_t) db->nreads+2) + db->path_len + 1 + (db->totlen + db->nreads + 4);
+}
+
+/* ---- -m mask tracks ------------------------------------------------------------------------ */
+
+typedef struct { int32_t b, e; } Ival;
+
+static int ival_cmp(const void *x, const void *y)
+{ const Ival *a = (const Ival *) x, *b = (const Ival *) y;
+  if (a->b != b->b) return (a->b < b->b ? -1 : 1);
+  return (a->e < b->e ? -1 : (a->e > b->e));
+}
+
+int dazz_add_mask(Dazz_Block *db, const char *track, const char *prog)
+{ char     path[4096];
+  FILE    *af = NULL, *df;
+  int      ispart = 0, tracklen, size, trimmed, first, count, i, n;
+  int      ureads, treads;
+  int64_t *anno, *noff;
+  int32_t *data, *npts;
+  int64_t  dbytes, total;
+
+  if (db->part > 0)
+    { snprintf(path,sizeof(path),"%s/.%s.%d.%s.anno",db->pwd,db->root,db->part,track);
+      if ((af = fopen(path,"r")) != NULL)
+        ispart = 1;
+    }
+  if (af == NULL)
+    { snprintf(path,sizeof(path),"%s/.%s.%s.anno",db->pwd,db->root,track);
+      af = fopen(path,"r");
+    }
+  if (af == NULL)
+    return (0);                                        /* Check_Track == -2: not for this DB */
+  if (fread(&tracklen,sizeof(int),1,af) != 1 || fread(&size,sizeof(int),1,af) != 1 || size < 0)
+    { fprintf(stderr,"%s: track files for %s are corrupted\n",prog,track);
+      fclose(af);
+      return (-1);
+    }
+  if (size != 0)
+    { fprintf(stderr,"%s: %s track is not a mask track.\n",prog,track);
+      fclose(af);
+      return (-1);
+    }
+  ureads = ispart ? db->ulast - db->ufirst : db->db_ureads;
+  treads = ispart ? db->nreads : db->db_treads;
+  if (tracklen == ureads)
+    trimmed = 0;
+  else if (tracklen == treads)
+    trimmed = 1;
+  else
+    { printf("%s: Warning: %s track not sync'd with db %s, ignored.\n",prog,track,db->root);
+      fclose(af);
+      return (0);
+    }
+  first = ispart ? 0 : (trimmed ? db->tfirst : db->ufirst);
+  count = trimmed ? db->nreads : db->ulast - db->ufirst;
+
+  anno = (int64_t *) malloc(sizeof(int64_t)*((size_t) count+1));
+  if (fseeko(af,(off_t) (8 + 8*(int64_t) first),SEEK_SET) != 0 ||
+      fread(anno,sizeof(int64_t),(size_t) count+1,af) != (size_t) count+1)
+    { fprintf(stderr,"%s: Track '%s' annotation file is junk\n",prog,track);
+      fclose(af); free(anno);
+      return (-1);
+    }
+  fclose(af);
+  if (ispart)
+    snprintf(path,sizeof(path),"%s/.%s.%d.%s.data",db->pwd,db->root,db->part,track);
+  else
+    snprintf(path,sizeof(path),"%s/.%s.%s.data",db->pwd,db->root,track);
+  dbytes = anno[count] - anno[0];
+  data = (int32_t *) malloc((size_t) dbytes + 8);
+  df = fopen(path,"r");
+  if (df == NULL || fseeko(df,(off_t) anno[0],SEEK_SET) != 0 ||
+      (dbytes > 0 && fread(data,1,(size_t) dbytes,df) != (size_t) dbytes))
+    { fprintf(stderr,"%s: Track '%s' data file is junk\n",prog,track);
+      if (df) fclose(df);
+      free(anno); free(data);
+      return (-1);
+    }
+  fclose(df);
+
+  /* union with what is there, read by read (damapper.c:181-343 computes the same point set up to
+     zero-length gaps between abutting intervals, which hold no k-mer) */
+  total = dbytes/4 + (db->mask_off ? db->mask_off[db->nreads] : 0);
+  noff = (int64_t *) malloc(sizeof(int64_t)*((size_t) db->nreads+1));
+  npts = (int32_t *) malloc(sizeof(int32_t)*((size_t) total+2));
+  { Ival *iv = (Ival *) malloc(sizeof(Ival)*((size_t) total/2+2));
+    int64_t top = 0;
+    n = 0;
+    for (i = 0; i < count; i++)
+      { int64_t j, m = 0;
+        if (!trimmed && !db->kept[i])
+          continue;
+        { const int64_t jb = (anno[i]-anno[0])/4, je = (anno[i+1]-anno[0])/4;
+          for (j = jb; j+1 < je; j += 2)
+            { iv[m].b = data[j]; iv[m].e = data[j+1]; m += 1; }
+        }
+        if (db->mask_off != NULL)
+          for (j = db->mask_off[n]; j+1 < db->mask_off[n+1]; j += 2)
+            { iv[m].b = db->mask_pts[j]; iv[m].e = db->mask_pts[j+1]; m += 1; }
+        qsort(iv,(size_t) m,sizeof(Ival),ival_cmp);
+        noff[n] = top;
+        for (j = 0; j < m; )
+          { int32_t b = iv[j].b, e = iv[j].e;
+            for (j += 1; j < m && iv[j].b <= e; j++)
+              if (iv[j].e > e) e = iv[j].e;
+            npts[top++] = b; npts[top++] = e;
+          }
+        n += 1;
+      }
+    noff[n] = top;
+    free(iv);
+  }
+  free(anno); free(data);
+  free(db->mask_off); free(db->mask_pts);
+  db->mask_off = noff; db->mask_pts = npts;
+  return (1);
 }

@@ -26,6 +26,13 @@ typedef struct
     int64_t *boff;        /* nreads+1 */
     int32_t *rlen;
     int64_t  path_len;    /* strlen(db->path) of the reference, enters sizeof_DB (DB.c:1050) */
+    /* what the mask loader needs of the untrimmed block */
+    int      ufirst, ulast;      /* untrimmed read range of the block in the whole DB */
+    int      db_ureads, db_treads;
+    uint8_t *kept;               /* ulast-ufirst flags: read survives the trim */
+    /* -m: union of the mask tracks found for this block (damapper.c:352-399), or NULL */
+    int64_t *mask_off;           /* nreads+1 offsets into mask_pts, counted in ints */
+    int32_t *mask_pts;
   } Dazz_Block;
 
 /* Reads the stub: fills root/pwd/isdam/nblocks/freq.  Returns 0, or -1 after printing why. */
@@ -35,6 +42,11 @@ int  dazz_load(const char *name, Dazz_Block *db);
 /* The same, but the reads stay 2-bit packed (db->packed/poff): the device expands them. */
 int  dazz_load_packed(const char *name, Dazz_Block *db);
 void dazz_close(Dazz_Block *db);
+/* Reads mask track `track` of the loaded block (block-level files first, then the whole-DB track;
+   trimmed or untrimmed, DB.c:1649-1702,1804-1990) and merges it into db->mask_off/mask_pts.
+   Returns 1 if the track was used, 0 if the DB has no such track or it is not in sync (a warning
+   is printed, damapper.c:364-367), -1 on error (after printing why). */
+int  dazz_add_mask(Dazz_Block *db, const char *track, const char *prog);
 /* In-place reverse complement of every read (complement_DB, damapper.c:433-469). */
 void dazz_complement(Dazz_Block *db);
 void dazz_view(const Dazz_Block *db, damgpu_block *view);

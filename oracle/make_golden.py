@@ -32,6 +32,31 @@ CASES = {
 }
 
 
+# -m: name -> (config, scale, seed, flags, kwargs); the tracks are dazzdb.random_masks(seed..):
+# "dust" on the reference and on the reads, "tan" on the reads only (so both get merged there)
+MASK_CASES = {
+    "c1_masks": ("C1", 0.03, 71, ("-C", "-mdust", "-mtan"), dict(do_b=1)),
+}
+
+
+def mask_tracks(contigs, rl, seed):
+    """(reference dust, reads dust, reads tan) for a mask case."""
+    glen = np.array([c.size for c in contigs], dtype=np.int64)
+    return (dazzdb.random_masks(glen, seed=seed + 1, max_intervals=40, max_len=2000),
+            dazzdb.random_masks(rl, seed=seed + 2, max_intervals=3, max_len=600),
+            dazzdb.random_masks(rl, seed=seed + 3, max_intervals=2, max_len=300))
+
+
+def write_mask_case(wd, contigs, rb, rl, seed):
+    ref = dazzdb.write_db(os.path.join(wd, "ref.dam"), contigs, is_dam=True)
+    rds = dazzdb.write_db(os.path.join(wd, "reads.db"), (rb, rl))
+    gd, rdust, rtan = mask_tracks(contigs, rl, seed)
+    dazzdb.write_mask_track(ref, "dust", *gd)
+    dazzdb.write_mask_track(rds, "dust", *rdust)
+    dazzdb.write_mask_track(rds, "tan", *rtan)
+    return gd, dazzdb.union_masks(rdust, rtan)
+
+
 def input_digest(contigs, rb, rl) -> str:
     h = hashlib.sha256()
     for c in contigs:
@@ -68,6 +93,22 @@ def main():
                             digest=np.array(input_digest(contigs, rb, rl)),
                             flags=np.array(" ".join(flags)))
         print(name, "records bytes", len(a), len(b), "prof", len(prof))
+    for name, (cfg, scale, seed, flags, kw) in MASK_CASES.items():
+        contigs, rb, rl = synth.make_config(cfg, scale=scale, seed=seed)
+        wd = tempfile.mkdtemp(prefix="golden_")
+        try:
+            write_mask_case(wd, contigs, rb, rl, seed)
+            r = run_ref.run_damapper(wd, "ref.dam", "reads.db", flags=flags, threads=4)
+            a = las.canonical_stream(r["m_files"])
+            b = las.canonical_stream(r["r_files"]) if r["r_files"] else b""
+        finally:
+            shutil.rmtree(wd, ignore_errors=True)
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"),
+                            a=np.frombuffer(a, dtype=np.uint8), b=np.frombuffer(b, dtype=np.uint8),
+                            prof=np.zeros(0, dtype=np.uint8),
+                            digest=np.array(input_digest(contigs, rb, rl)),
+                            flags=np.array(" ".join(flags)))
+        print(name, "records bytes", len(a), len(b))
 
 
 if __name__ == "__main__":

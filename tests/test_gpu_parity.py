@@ -290,6 +290,48 @@ def test_mask_tracks(api, oracle_mod, cfg, scale, seed, kw):
     assert g["a"] == o["a"] and g["b"] == o["b"] and g["prof"] == o["prof"]
 
 
+def test_mask_tracks_match_reference_golden(api, tmp_path):
+    """-m end to end against the unmodified reference (fixture c1_masks: damapper -C -mdust -mtan):
+    through the API with the merged masks, and through the host driver, which reads the .anno/.data
+    track files itself and merges the two tracks of the reads DB."""
+    import subprocess
+    from damapper_b200 import dazzdb, las
+    from oracle import make_golden as mg
+    cfg, scale, seed, flags, kw = mg.MASK_CASES["c1_masks"]
+    contigs, rb, rl, rd, rf, rc = make_case(cfg, scale, seed)
+    g = np.load(os.path.join(GOLDEN, "c1_masks.npz"))
+    assert mg.input_digest(contigs, rb, rl) == str(g["digest"])
+    gd, rdust, rtan = mg.mask_tracks(contigs, rl, seed)
+    rm = dazzdb.union_masks(rdust, rtan)
+    out = api.map_block(api.HostBlock(*rd, mask=rm), [api.HostBlock(*rf, mask=gd)], api.HostBlock(*rf),
+                        freq=base_freq(contigs), **kw)
+    assert out["a"] == g["a"].tobytes() and out["b"] == g["b"].tobytes()
+    # the driver
+    exe = os.path.join(ROOT, "damapper_b200", "damapper")
+    wd = str(tmp_path)
+    mg.write_mask_case(wd, contigs, rb, rl, seed)
+    bindir, keep = os.path.join(wd, "bin"), os.path.join(wd, "keep")
+    os.makedirs(bindir); os.makedirs(keep); os.makedirs(os.path.join(wd, "tmp"))
+    with open(os.path.join(bindir, "LAsort"), "w") as f:
+        f.write('#!/bin/bash\nfor a in "$@"; do case "$a" in -*) ;; *) pat="$a";; esac; done\n'
+                'for f in ${pat/@/[0-9]*}; do [ -e "$f" ] && cp "$f" "%s"/; done\nexit 0\n' % keep)
+    for n in ("LAcat", "LAmerge"):
+        with open(os.path.join(bindir, n), "w") as f:
+            f.write("#!/bin/bash\nexit 0\n")
+    for n in ("LAsort", "LAcat", "LAmerge"):
+        os.chmod(os.path.join(bindir, n), 0o755)
+    env = dict(os.environ)
+    env["PATH"] = bindir + os.pathsep + env["PATH"]
+    p = subprocess.run([exe, "-T4", "-P" + os.path.join(wd, "tmp")] + list(flags) + ["-mnone", "ref.dam", "reads.db"],
+                       cwd=wd, env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr
+    assert "Track none given but never used" in p.stdout
+    m = [os.path.join(keep, "reads.ref.M%d.las" % i) for i in range(1, 5)]
+    r = [os.path.join(keep, "ref.reads.R%d.las" % i) for i in range(1, 5)]
+    assert las.canonical_stream(m) == g["a"].tobytes()
+    assert las.canonical_stream(r) == g["b"].tobytes()
+
+
 def test_packed_bps_upload_decodes_on_the_device(api, oracle_mod):
     """the .bps image (2 bits per base) expanded on the device gives the
     Load_All_Reads image byte for byte, for ragged read lengths (all residues mod 4), and the

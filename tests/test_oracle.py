@@ -121,6 +121,31 @@ def test_empty_and_degenerate_inputs(oracle_mod):
     assert recs[0]["flags"] == 0x14        # START | BEST
 
 
+def _mask_case(orc_or_api, name):
+    """Blocks of a -m golden case: (reads, [ref fwd (, ref rc)], whole ref, freq, kwargs)."""
+    from damapper_b200 import dazzdb
+    from oracle import make_golden as mg
+    cfg, scale, seed, flags, kw = mg.MASK_CASES[name]
+    contigs, rb, rl, rd, rf, rc = make_case(cfg, scale, seed)
+    gd, rdust, rtan = mg.mask_tracks(contigs, rl, seed)
+    rm = dazzdb.union_masks(rdust, rtan)
+    gc = dazzdb.mirror_masks(gd[0], gd[1], rf[2])
+    return contigs, rb, rl, (rd, rm), (rf, gd), (rc, gc), kw
+
+
+def test_oracle_masks_match_golden(oracle_mod):
+    """-m: the oracle's masked extraction + mirrored reference mask against the unmodified
+    reference run with -mdust -mtan (two tracks on the reads: merged)."""
+    from oracle.make_golden import input_digest
+    orc = oracle_mod
+    contigs, rb, rl, (rd, rm), (rf, gd), (rc, gc), kw = _mask_case(orc, "c1_masks")
+    g = np.load(os.path.join(GOLDEN, "c1_masks.npz"))
+    assert input_digest(contigs, rb, rl) == str(g["digest"])
+    out = orc.map_block(orc.HostBlock(*rd, mask=rm), [(orc.HostBlock(*rf, mask=gd), orc.HostBlock(*rc, mask=gc))],
+                        orc.HostBlock(*rf), freq=base_freq(contigs), **kw)
+    assert out["a"] == g["a"].tobytes() and out["b"] == g["b"].tobytes()
+
+
 def _have_ref():
     from oracle import run_ref
     return run_ref.have_ref()
