@@ -27,6 +27,7 @@ static float       g_sort_times[3] = { 0, 0, 0 };
 Params g_par;          // filter parameters + the map.h globals
 bool   g_trace = false;
 int    g_align_tier = 0, g_align_slots = 4;
+bool   g_chain_async = true;
 
 void trace_mark(const char *name)
 { static double last = 0;
@@ -148,6 +149,7 @@ int damgpu_init(int device)
   g_trace = (getenv("DAMGPU_TRACE") != nullptr);
   if (const char *t = getenv("DAMGPU_ALIGN"))
     g_align_tier = !strcmp(t, "warp") ? 0 : !strcmp(t, "lane") ? 1 : !strcmp(t, "group") ? 3 : 2;
+  g_chain_async = (getenv("DAMGPU_SYNC_CHAIN") == nullptr);
   if (const char *t = getenv("DAMGPU_SLOTS"))
     g_align_slots = atoi(t);
   g_ready = true;
@@ -303,7 +305,7 @@ void damgpu_mapper_free(damgpu_mapper *mm)
 void damgpu_mapper_chain(damgpu_mapper *mm, const damgpu_seeds *s, int bstart, int comp, int start)
 { MapperH *h = reinterpret_cast<MapperH *>(mm);
   if (start) mapper_reset(h->m);
-  chain_seeds(h->m, reinterpret_cast<const SeedSet *>(s), bstart, comp, 0);
+  chain_seeds(h->m, const_cast<SeedSet *>(reinterpret_cast<const SeedSet *>(s)), bstart, comp, 0, false);
 }
 
 void damgpu_mapper_match(damgpu_mapper *mm, const damgpu_dblock *ref, const damgpu_index *ref_idx,
@@ -323,7 +325,7 @@ void damgpu_mapper_match(damgpu_mapper *mm, const damgpu_dblock *ref, const damg
       fflush(stdout);
     }
   if (start) mapper_reset(h->m);
-  chain_seeds(h->m, ss, rb->tfirst, comp, 0);
+  chain_seeds(h->m, ss, rb->tfirst, comp, 0, g_chain_async);
   free_seeds(ss);
 }
 
@@ -334,6 +336,7 @@ int64_t damgpu_mapper_last_hits(const damgpu_mapper *mm)
 static void fetch_pool(const Mapper *m, std::vector<Candidate> &cand, std::vector<int> &head,
                        std::vector<uint32_t> &jumps)
 { int ctop = 0; unsigned long long jtop = 0;
+  chain_sync();
   CUDA_CHECK(cudaMemcpy(&ctop, m->cand_top, sizeof(int), cudaMemcpyDeviceToHost));
   CUDA_CHECK(cudaMemcpy(&jtop, m->jump_top, sizeof(jtop), cudaMemcpyDeviceToHost));
   cand.resize(ctop); head.resize(m->reads->nreads); jumps.resize(jtop);
@@ -382,6 +385,7 @@ int64_t damgpu_mapper_get_candidates(const damgpu_mapper *mm, damgpu_candidate *
 int64_t damgpu_mapper_get_cover(const damgpu_mapper *mm, int16_t *out, int64_t max)
 { const Mapper *m = reinterpret_cast<const MapperH *>(mm)->m;
   const int64_t tot = m->h_coff[m->reads->nreads];
+  chain_sync();
   if (out != nullptr)
     CUDA_CHECK(cudaMemcpy(out, m->cover, sizeof(int16_t) * (size_t) (tot < max ? tot : max),
                           cudaMemcpyDeviceToHost));

@@ -8,6 +8,7 @@
 // hence no per-thread sizing).  Candidates and their Jump lists persist in device pools
 // across Match_Filter calls; per-read list heads replace DAZZ_READ.coff (map.c:1875).
 #include <algorithm>
+#include <vector>
 #include "common.cuh"
 #include "mapper.cuh"
 
@@ -299,6 +300,36 @@ k_chain(const SeedPair *__restrict__ hits, int64_t nhits, int nreads, int K, int
   if (lane == 0) head[ar] = chead;
 }
 
+// ---- the chain kernel runs on its own stream -------------------------------------------------
+// k_chain is bound by the latency of its longest read (about 1 ms on the bench workload whatever
+// the number of reads) and leaves most of the machine idle; nothing that follows on the main
+// stream until the next chain call or the Reporter touches what it reads or writes (seeds,
+// scratch, candidate/jump pools, list heads, -p counters).  So it is launched on a second,
+// non-blocking stream and the complement + index + merge-join of the next orientation overlap it.
+// Buffers it uses are released only after the main stream has been made to wait for it.
+struct ChainAsync
+{ cudaStream_t stream = nullptr;
+  cudaEvent_t  ready = nullptr, done = nullptr;
+  bool         busy = false;
+  std::vector<void *> pending;
+};
+static ChainAsync g_ca;
+
+static void chain_release(cudaStream_t main_stream, bool host_wait)
+{ if (!g_ca.busy)
+    return;
+  if (host_wait)
+    CUDA_CHECK(cudaStreamSynchronize(g_ca.stream));
+  else
+    CUDA_CHECK(cudaStreamWaitEvent(main_stream, g_ca.done, 0));
+  for (void *p : g_ca.pending)
+    dfree(p);
+  g_ca.pending.clear();
+  g_ca.busy = false;
+}
+
+void chain_sync() { chain_release(0, true); }
+
 static void ensure_pools(Mapper *m, int64_t nhits)
 { // a candidate is the best end of a distinct chain origin with >= 3 seeds and the from-paths
   // of distinct origins are disjoint: at most nhits/3 new candidates and nhits new jumps
@@ -306,7 +337,8 @@ static void ensure_pools(Mapper *m, int64_t nhits)
   // nhits jumps.  The true tops are fetched only when a pool has to grow.
   int h_ctop = m->ctop_bound; unsigned long long h_jtop = m->jtop_bound;
   if ((int64_t) h_ctop + nhits / 3 + 16 > m->cand_cap || h_jtop + (uint64_t) nhits + 16 > m->jump_cap)
-    { CUDA_CHECK(cudaMemcpy(&h_ctop, m->cand_top, sizeof(int), cudaMemcpyDeviceToHost));
+    { chain_sync();                                      // the pools are about to be read and moved
+      CUDA_CHECK(cudaMemcpy(&h_ctop, m->cand_top, sizeof(int), cudaMemcpyDeviceToHost));
       CUDA_CHECK(cudaMemcpy(&h_jtop, m->jump_top, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     }
   int64_t need_c = (int64_t) h_ctop + nhits / 3 + 16;
@@ -360,6 +392,7 @@ Mapper *mapper_new(const DeviceBlock *reads)
 
 void mapper_reset(Mapper *m)                           // start != 0, map.c:1574-1588,1491-1506
 { const int n = m->reads->nreads;
+  chain_sync();
   CUDA_CHECK(cudaMemset(m->head, 0xff, sizeof(int) * ((size_t) n + 1)));
   CUDA_CHECK(cudaMemset(m->cand_top, 0, sizeof(int) * 4));
   CUDA_CHECK(cudaMemset(m->jump_top, 0, sizeof(unsigned long long) * 2));
@@ -370,17 +403,24 @@ void mapper_reset(Mapper *m)                           // start != 0, map.c:1574
 
 void mapper_free(Mapper *m)
 { if (m == nullptr) return;
+  chain_sync();
   dfree(m->head); dfree(m->cand_top); dfree(m->jump_top); dfree(m->overflow);
   dfree(m->coff); dfree(m->cover); dfree(m->cand); dfree(m->jumps);
   delete m;
 }
 
-void chain_seeds(Mapper *m, const SeedSet *ss, int bstart, int comp, cudaStream_t stream)
+void chain_seeds(Mapper *m, SeedSet *ss, int bstart, int comp, cudaStream_t stream, bool async)
 { const int64_t nhits = ss->nhits;
   if (nhits == 0) return;
   if (m->spacing != g_par.spacing)
     fatal("SPACING changed after the mapper was created");
+  if (g_ca.stream == nullptr)
+    { CUDA_CHECK(cudaStreamCreateWithFlags(&g_ca.stream, cudaStreamNonBlocking));
+      CUDA_CHECK(cudaEventCreateWithFlags(&g_ca.ready, cudaEventDisableTiming));
+      CUDA_CHECK(cudaEventCreateWithFlags(&g_ca.done, cudaEventDisableTiming));
+    }
   TRACE(nullptr);
+  chain_release(stream, false);                        // the previous call's buffers go back now
   ensure_pools(m, nhits);
   TRACE("chain: ensure_pools");
   ChainScratch sc;
@@ -389,10 +429,21 @@ void chain_seeds(Mapper *m, const SeedSet *ss, int bstart, int comp, cudaStream_
   sc.dead = scratch + 3 * nhits; sc.E = scratch + 4 * nhits;
   sc.S = dalloc<int4>((size_t) nhits);
   const int n = m->reads->nreads;
-  LAUNCH(k_chain, (n + CH_WARPS - 1) / CH_WARPS, CH_WARPS * 32, 0, stream, ss->hits, nhits, n, g_par.kmer, bstart, comp,
-         g_par.profile, g_par.spacing, sc, m->cand, m->cand_top, m->cand_cap, m->jumps,
+  CUDA_CHECK(cudaEventRecord(g_ca.ready, stream));     // seeds, pools and scratch are ready
+  CUDA_CHECK(cudaStreamWaitEvent(g_ca.stream, g_ca.ready, 0));
+  LAUNCH(k_chain, (n + CH_WARPS - 1) / CH_WARPS, CH_WARPS * 32, 0, g_ca.stream, ss->hits, nhits, n, g_par.kmer,
+         bstart, comp, g_par.profile, g_par.spacing, sc, m->cand, m->cand_top, m->cand_cap, m->jumps,
          m->jump_top, (unsigned long long) m->jump_cap, m->head, m->cover, m->coff, m->overflow);
-  dfree(scratch); dfree(sc.S);                        // stream-ordered: reused only by later launches
+  CUDA_CHECK(cudaEventRecord(g_ca.done, g_ca.stream));
+  g_ca.busy = true;
+  g_ca.pending.push_back(scratch);
+  g_ca.pending.push_back(sc.S);
+  if (async)                                           // the seeds now belong to the pending call
+    { g_ca.pending.push_back(ss->hits);
+      ss->hits = nullptr;
+    }
+  else
+    chain_sync();
   TRACE("chain: kernel");
   // m->overflow (internal sizing error, cannot happen with the bounds above) is checked by the
   // Reporter, which has to synchronise anyway

@@ -58,6 +58,7 @@ extern bool g_trace;
 // (align_lane.cu), 2 = several jobs per warp, diagonals packed onto the lanes (align_pack.cu).
 // DAMGPU_ALIGN=warp|lane|pack and DAMGPU_SLOTS=2|4|8 override (development).
 extern int g_align_tier, g_align_slots;
+extern bool g_chain_async;         // chain kernel on its own stream (DAMGPU_SYNC_CHAIN=1 turns it off)
 
 // ---- radix_sort.cu -------------------------------------------------------------------
 // Stable LSD radix sort of n 16-byte records on the key bytes listed in `bytes` (least

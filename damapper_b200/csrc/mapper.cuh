@@ -51,6 +51,9 @@ Mapper *mapper_new(const DeviceBlock *reads);
 void    mapper_reset(Mapper *m);
 void    mapper_free(Mapper *m);
 // chain_thread over all reads for the sorted seeds of one Match_Filter call
-void    chain_seeds(Mapper *m, const SeedSet *ss, int bstart, int comp, cudaStream_t stream);
+// With async the kernel runs on the chain stream, takes ownership of ss->hits and the call returns at
+// once; chain_sync() waits for it (every reader of the candidate pools calls it first).
+void    chain_seeds(Mapper *m, SeedSet *ss, int bstart, int comp, cudaStream_t stream, bool async);
+void    chain_sync();
 
 }  // namespace damgpu

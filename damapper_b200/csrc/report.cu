@@ -641,6 +641,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   if (m->spacing != S)
     fatal("SPACING changed after the mapper was created");
 
+  chain_sync();                                          // the last chain call may still be running
   TRACE(nullptr);
   // alignment spec tables
   std::vector<int16_t> tables(65536);
