@@ -641,7 +641,6 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   if (m->spacing != S)
     fatal("SPACING changed after the mapper was created");
 
-  chain_sync();                                          // the last chain call may still be running
   TRACE(nullptr);
   // alignment spec tables
   std::vector<int16_t> tables(65536);
@@ -654,6 +653,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   rc.raw = dalloc<uint8_t>((size_t) rd->total + 2 * BLOCK_SLACK);
   rc.bases = rc.raw + BLOCK_SLACK;
   revcomp_copy_block(rd, rc.bases, stream);
+  chain_sync();                                          // the last chain call may still be running
 
   TRACE("report: spec+rc copy");
   // jobs = live candidates in (read, list order)
