@@ -1061,6 +1061,134 @@ k_pass_v9(const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t n, uin
 #undef DIG9
 }
 
+// ---------------- V10 (v9 + mixed matcher / highest-lane leader): v8 + PRMT digits (word as template), unchecked loads on full tiles, lean probe-8 look-back ----------------
+template <int THREADS, int ITEMS, int MINB, int PROBE, int W32, int MIX, int LH>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_pass_v10(const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t n, uint32_t psel,
+          const uint32_t *__restrict__ gbase, uint32_t *tile_state, uint32_t *tile_counter)
+{ constexpr int NB = 256, WARPS = THREADS / 32, TILE = THREADS * ITEMS;
+  extern __shared__ uint4 dyn[];
+  uint4    *stage = dyn;
+  uint32_t *whist = reinterpret_cast<uint32_t *>(dyn);
+  __shared__ uint32_t s_wsum[WARPS];
+  __shared__ uint32_t s_tile;
+#define DIG9(r) __byte_perm((W32 == 0) ? (r).x : (W32 == 1) ? (r).y : (W32 == 2) ? (r).z : (r).w, 0, psel)
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lt = (1u << lane) - 1;
+  if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+  uint32_t *wh = whist + warp * NB;
+#pragma unroll
+  for (int i = lane; i < NB; i += 32) wh[i] = 0;
+  __syncthreads();
+  const uint32_t tile  = s_tile;
+  const uint32_t tbase = tile * (uint32_t) TILE;
+  const uint32_t nvalid = (n - tbase < (uint32_t) TILE) ? n - tbase : (uint32_t) TILE;
+  const uint4 *src = in + tbase + warp * (32 * ITEMS) + lane;
+
+  uint4 rec[ITEMS];
+  if (nvalid == (uint32_t) TILE)
+    {
+#pragma unroll
+      for (int i = 0; i < ITEMS; i++) rec[i] = __ldcs(src + i * 32);
+    }
+  else
+    { const uint32_t base = tbase + warp * (32 * ITEMS) + lane;
+#pragma unroll
+      for (int i = 0; i < ITEMS; i++)
+        rec[i] = (base + i * 32 < n) ? __ldcs(src + i * 32) : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    }
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++)
+    atomicAdd(&wh[DIG9(rec[i])], 1u);
+  __syncthreads();
+
+  uint32_t cnt = 0, dbase;
+  uint32_t *st = tile_state + (size_t) tile * 256 + (tid & 255);
+  if (tid < 256)
+    {
+#pragma unroll
+      for (int w = 0; w < WARPS; w++) cnt += whist[w * 256 + tid];
+      if (tid == 255) cnt -= (uint32_t) TILE - nvalid;
+      st_relaxed(st, (tile == 0 ? FLAG_INC : FLAG_AGG) | cnt);
+    }
+  { uint32_t x = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_wsum[warp] = x;
+    __syncthreads();
+    uint32_t add = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; w++) if (w < warp) add += s_wsum[w];
+    dbase = x + add - cnt;
+  }
+  if (tid < 256)
+    { uint32_t run = dbase;
+#pragma unroll
+      for (int w = 0; w < WARPS; w++) { const uint32_t c = whist[w * 256 + tid]; whist[w * 256 + tid] = run; run += c; }
+    }
+  __syncthreads();
+
+  uint32_t pos[ITEMS];
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++)
+    { const uint32_t dig   = DIG9(rec[i]);
+      const uint32_t peers = (MIX > 0 && (i % MIX) == MIX - 1) ? __match_any_sync(0xffffffffu, dig) : match_ballot2<8>(dig);
+      uint32_t old = 0;
+      if (LH)
+        { const int leader = 31 - __clz(peers);
+          if (lane == leader) old = atomicAdd(&wh[dig], (uint32_t) __popc(peers));
+          pos[i] = __shfl_sync(0xffffffffu, old, leader) + __popc(peers & lt);
+        }
+      else
+        { if ((peers & lt) == 0) old = atomicAdd(&wh[dig], (uint32_t) __popc(peers));
+          pos[i] = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1) + __popc(peers & lt);
+        }
+    }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++) stage[pos[i]] = rec[i];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+
+  uint32_t gdst = 0;
+  if (tid < 256)
+    { uint32_t excl = 0;
+      if (tile > 0)
+        { const uint32_t *p = tile_state + (size_t) (tile - 1) * 256 + tid;
+          uint32_t left = tile;
+          while (true)
+            { uint32_t v[PROBE];
+#pragma unroll
+              for (int k = 0; k < PROBE; k++)
+                v[k] = ((uint32_t) k < left) ? ld_relaxed(p - (size_t) k * 256) : FLAG_INC;
+              uint32_t adv = 0; bool stop = false, inc = false;
+#pragma unroll
+              for (int k = 0; k < PROBE; k++)
+                if (!stop)
+                  { if (v[k] == 0) stop = true;                       // not published yet
+                    else
+                      { excl += v[k] & VAL_MASK; adv += 1;
+                        if (v[k] & FLAG_INC) { stop = true; inc = true; }
+                      }
+                  }
+              if (inc) break;
+              p -= (size_t) adv * 256; left -= adv;
+            }
+          st_relaxed(st, FLAG_INC | (excl + cnt));
+        }
+      gdst = gbase[tid] + excl;
+    }
+  __syncthreads();
+  if (tid < 256 && cnt > 0)
+    { const uint32_t sa = (uint32_t) __cvta_generic_to_shared(stage + dbase);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                   :: "l"(out + gdst), "r"(sa), "r"(cnt * 16u) : "memory");
+    }
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#undef DIG9
+}
+
 // ---------------- V5: early counts + ballot ranking straight to staged positions + probes + TMA store ----------------
 template <int THREADS, int ITEMS, int BITS, int MINB, int PROBE>
 __global__ void __launch_bounds__(THREADS, MINB)
@@ -1735,6 +1863,21 @@ static void L_v9(Ctx &c, const uint4 *s, uint4 *d, int word, int shift, uint32_t
   else          k_pass_v9<THREADS, ITEMS, MINB, PROBE, 1><<<ntiles, THREADS, smem>>>(s, d, c.n, psel, c.hist + p * 256, c.state, c.state + (size_t) ntiles * 256);
 }
 
+template <int THREADS, int ITEMS, int MINB, int PROBE, int MIX, int LH>
+static void L_v10(Ctx &c, const uint4 *s, uint4 *d, int word, int shift, uint32_t ntiles, int p)
+{ const size_t smem = (size_t) THREADS * ITEMS * 16;
+  const int byte = word * 8 + shift / 8, w32 = byte >> 2;
+  const uint32_t psel = 0x4440u | (uint32_t) (byte & 3);
+  static bool set = false;
+  if (!set)
+    { CK(cudaFuncSetAttribute(k_pass_v10<THREADS, ITEMS, MINB, PROBE, 0, MIX, LH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      CK(cudaFuncSetAttribute(k_pass_v10<THREADS, ITEMS, MINB, PROBE, 1, MIX, LH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      set = true;
+    }
+  if (w32 == 0) k_pass_v10<THREADS, ITEMS, MINB, PROBE, 0, MIX, LH><<<ntiles, THREADS, smem>>>(s, d, c.n, psel, c.hist + p * 256, c.state, c.state + (size_t) ntiles * 256);
+  else          k_pass_v10<THREADS, ITEMS, MINB, PROBE, 1, MIX, LH><<<ntiles, THREADS, smem>>>(s, d, c.n, psel, c.hist + p * 256, c.state, c.state + (size_t) ntiles * 256);
+}
+
 int main(int argc, char **argv)
 { uint32_t n = argc > 1 ? (uint32_t) atoll(argv[1]) : 139813248u;
   const char *which = argc > 2 ? argv[2] : "all";
@@ -1886,5 +2029,11 @@ int main(int argc, char **argv)
   if (want("v9e")) run_timed("v9 256x12 probe8", c, 8, 5, 3072, true, L_v9<256, 12, 3, 8>);
   if (want("v9f")) run_timed("v9 256x16 probe8", c, 8, 5, 4096, true, L_v9<256, 16, 2, 8>);
   if (want("v9g")) run_timed("v9 384x12 probe16", c, 8, 5, 4608, true, L_v9<384, 12, 2, 16>);
+  if (want("v10a")) run_timed("v10 384x12 ballots, ffs leader (=v9)", c, 8, 5, 4608, true, L_v10<384, 12, 2, 8, 0, 0>);
+  if (want("v10b")) run_timed("v10 384x12 ballots, highest-lane leader", c, 8, 5, 4608, true, L_v10<384, 12, 2, 8, 0, 1>);
+  if (want("v10c")) run_timed("v10 384x12 every 4th MATCH.ANY", c, 8, 5, 4608, true, L_v10<384, 12, 2, 8, 4, 1>);
+  if (want("v10d")) run_timed("v10 384x12 every 3rd MATCH.ANY", c, 8, 5, 4608, true, L_v10<384, 12, 2, 8, 3, 1>);
+  if (want("v10e")) run_timed("v10 384x12 every 6th MATCH.ANY", c, 8, 5, 4608, true, L_v10<384, 12, 2, 8, 6, 1>);
+  if (want("v10f")) run_timed("v10 384x12 every 2nd MATCH.ANY", c, 8, 5, 4608, true, L_v10<384, 12, 2, 8, 2, 1>);
   return 0;
 }
