@@ -21,8 +21,38 @@ struct ChainScratch                 // one slot per seed
   int4 *S;                          // spill area of the active set (node, diag, apos, -)
 };
 
-constexpr int CH_WARPS = 8;         // reads per CTA
-constexpr int CH_SCAP  = 128;       // active-set entries kept in shared memory per warp
+constexpr int CH_WARPS = 4;         // reads in flight per CTA
+constexpr int CH_SCAP  = 64;        // active-set entries kept in shared memory per warp (general path)
+constexpr int CH_NCAP  = 512;       // chain nodes kept in shared memory per warp (fast path)
+constexpr int CH_CTAS  = 6;         // CTAs per SM the shared memory allows (37 KB each)
+
+// A chain node of the fast path: everything the inner loop and the candidate walk read about a seed
+// in one 16-byte shared-memory word (the general path keeps from/orig/cost/dead in global scratch).
+struct __align__(16) NodeSm
+{ int cost, apos, diag;
+  short from;
+  unsigned short od;                // orig | dead << 15
+};
+
+// node accessors of the two paths (same interface)
+struct AccG
+{ const SeedPair *hits; int64_t g0; int *from_; const int *orig_, *cost_;
+  __device__ __forceinline__ int  apos(int n) const { return hits[g0 + n].apos + 1; }
+  __device__ __forceinline__ int  bpos(int n) const { return hits[g0 + n].apos + 1 - hits[g0 + n].diag; }
+  __device__ __forceinline__ int  from(int n) const { return from_[n]; }
+  __device__ __forceinline__ void set_from(int n, int v) const { from_[n] = v; }
+  __device__ __forceinline__ int  orig(int n) const { return orig_[n]; }
+  __device__ __forceinline__ int  cost(int n) const { return cost_[n]; }
+};
+struct AccS
+{ NodeSm *N;
+  __device__ __forceinline__ int  apos(int n) const { return N[n].apos; }
+  __device__ __forceinline__ int  bpos(int n) const { return N[n].apos - N[n].diag; }
+  __device__ __forceinline__ int  from(int n) const { return N[n].from; }
+  __device__ __forceinline__ void set_from(int n, int v) const { N[n].from = (short) v; }
+  __device__ __forceinline__ int  orig(int n) const { return N[n].od & 0x7fff; }
+  __device__ __forceinline__ int  cost(int n) const { return N[n].cost; }
+};
 
 // remove the entry with key (d,a) from the sorted active set; all lanes, uniform
 __device__ __forceinline__ void set_remove(int4 *S, int &ns, int d, int a, int lane)
@@ -46,17 +76,16 @@ __device__ __forceinline__ void set_remove(int4 *S, int &ns, int d, int a, int l
 }
 
 // Candidate test + dominance filter + Jump list for chain end h (map.c:1642-1767); one lane
-__device__ void consider(const SeedPair *__restrict__ hits, int64_t g0, int h, int ar, int br,
-                         int comp, int K, int profile, int spacing, int *from, const int *orig,
-                         const int *cost, Candidate *cand, int *cand_top, int cand_cap,
+template <class Acc>
+__device__ void consider(const Acc nd, int h, int ar, int br,
+                         int comp, int K, int profile, int spacing,
+                         Candidate *cand, int *cand_top, int cand_cap,
                          uint32_t *jumps, unsigned long long *jump_top, unsigned long long jump_cap,
                          int &chead, int16_t *cover, const int64_t *coff, int *overflow)
-{
-#define APOS(n) (hits[g0 + (n)].apos + 1)
-#define BPOS(n) (hits[g0 + (n)].apos + 1 - hits[g0 + (n)].diag)
-  const int ab = APOS(orig[h]) - K, bb = BPOS(orig[h]) - K;
-  const int ae = APOS(h), be = BPOS(h);
-  const int hc = cost[h];
+{ const int oh = nd.orig(h);
+  const int ab = nd.apos(oh) - K, bb = nd.bpos(oh) - K;
+  const int ae = nd.apos(h), be = nd.bpos(h);
+  const int hc = nd.cost(h);
 
   if (profile)                                  // map.c:1654-1666
     { int16_t *cnt = cover + coff[ar];
@@ -94,13 +123,17 @@ __device__ void consider(const SeedPair *__restrict__ hits, int64_t g0, int h, i
   D->afirst = ab; D->alast = ae; D->bfirst = bb; D->blast = be;
 
   int len = 0;                                  // chain_length, map.c:1243-1260 (splices persist)
-  { int x = h, y = from[h];
+  { int x = h, y = nd.from(h);
+    int ax = nd.apos(x), bx = nd.bpos(x);
     while (y >= 0)
-      { const int da = APOS(x) - APOS(y);
-        if (da == BPOS(x) - BPOS(y) && da < 100)
-          y = from[x] = from[y];
+      { const int ay = nd.apos(y), by = nd.bpos(y);
+        const int da = ax - ay;
+        if (da == bx - by && da < 100)
+          { y = nd.from(y);
+            nd.set_from(x, y);
+          }
         else
-          { len += 1; x = y; y = from[x]; }
+          { len += 1; x = y; ax = ay; bx = by; y = nd.from(x); }
       }
   }
   D->length = len;
@@ -109,195 +142,362 @@ __device__ void consider(const SeedPair *__restrict__ hits, int64_t g0, int h, i
     { jo = atomicAdd(jump_top, (unsigned long long) len);
       if (jo + len > jump_cap) { *overflow = 1; return; }
       int g = h, k = 0;
-      for (int f = from[h]; f >= 0; f = from[f])          // map.c:1746-1759
-        { const uint32_t da = (uint16_t) (APOS(g) - APOS(f));
-          const uint32_t db = (uint16_t) (BPOS(g) - BPOS(f));
+      int ag = nd.apos(g), bg = nd.bpos(g);
+      for (int f = nd.from(h); f >= 0; f = nd.from(f))    // map.c:1746-1759
+        { const int af = nd.apos(f), bf = nd.bpos(f);
+          const uint32_t da = (uint16_t) (ag - af);
+          const uint32_t db = (uint16_t) (bg - bf);
           jumps[jo + k++] = da | (db << 16);
-          g = f;
+          g = f; ag = af; bg = bf;
         }
     }
   D->chain = (long long) jo;
-#undef APOS
-#undef BPOS
 }
 
-// One warp per read.  The lanes scan the sorted active set 32 entries at a time (insert position,
-// predOf/leftmost, succOf, removals); everything else is warp-uniform scalar work.
+// One warp per read, reads handed out by a counter (a read with its true location in this
+// orientation carries ~10x the seeds of one without).  A (read, contig) group starts on the FAST
+// path: the active set is one entry per lane in registers (insert / remove / predOf / leftmost /
+// succOf are a ballot and a shuffle each) and the chain nodes sit in shared memory.  When the set
+// would pass 32 entries or the group 512 nodes, the state is written out and the GENERAL path takes
+// over for the rest of the group: sorted slice in shared memory (spilling to global scratch), nodes
+// in global scratch, the lanes scan the slice 32 entries at a time.  Both give the same result.
 __global__ void __launch_bounds__(CH_WARPS * 32)
 k_chain(const SeedPair *__restrict__ hits, int64_t nhits, int nreads, int K, int bstart, int comp,
         int profile, int spacing, ChainScratch sc, Candidate *cand, int *cand_top, int cand_cap,
         uint32_t *jumps, unsigned long long *jump_top, unsigned long long jump_cap,
-        int *head, int16_t *cover, const int64_t *__restrict__ coff, int *overflow)
-{ __shared__ int4 s_S[CH_WARPS][CH_SCAP];
+        int *head, int16_t *cover, const int64_t *__restrict__ coff, int *overflow, int *read_counter)
+{ __shared__ int4   s_S[CH_WARPS][CH_SCAP];
+  __shared__ NodeSm s_N[CH_WARPS][CH_NCAP];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ar = blockIdx.x * CH_WARPS + warp;
-  if (ar >= nreads) return;
-
-  int64_t lo = 0, hi = nhits;                        // seed range of read ar
-  while (lo < hi)
-    { int64_t mid = (lo + hi) >> 1;
-      if (hits[mid].aread < ar) lo = mid + 1; else hi = mid;
-    }
-  int64_t nidx = lo;
-  if (nidx >= nhits || hits[nidx].aread != ar) return;
-
   const int hithr = HITMIN * K;
-  int chead = head[ar];
+  const unsigned FULL = 0xffffffffu;
 
-  while (nidx < nhits && hits[nidx].aread == ar)
-    { const int     br = hits[nidx].bread;
-      const int64_t g0 = nidx;                         // group base: node n <-> seed g0+n
-      int *from = sc.from + g0, *orig = sc.orig + g0, *cost = sc.cost + g0, *dead = sc.dead + g0;
-      int *E = sc.E + g0;
-      int4 *S = s_S[warp];
-      bool spilled = false;
-      int nn = 0, ns = 0, nexp = 0, qhead = 0;
+  while (true)
+  { int ar = 0;
+    if (lane == 0) ar = atomicAdd(read_counter, 1);
+    ar = __shfl_sync(FULL, ar, 0);
+    if (ar >= nreads) break;
 
-      for ( ; nidx < nhits; nidx++)
-        { const SeedPair hp = hits[nidx];
-          if (hp.aread != ar || hp.bread != br) break;
-          const int apos = hp.apos + 1;
-          const int diag = hp.diag;
-          const int bpos = apos - diag;
+    int64_t lo = 0, hi = nhits;                        // seed range of read ar
+    while (lo < hi)
+      { int64_t mid = (lo + hi) >> 1;
+        if (hits[mid].aread < ar) lo = mid + 1; else hi = mid;
+      }
+    int64_t nidx = lo;
+    if (nidx >= nhits || hits[nidx].aread != ar) continue;
 
-          while (qhead < nn && hits[g0 + qhead].apos + 1 < apos - MAX_GAP)   // map.c:1787-1796
-            { const int q = qhead++;
-              if (!dead[q])
-                { set_remove(S, ns, hits[g0 + q].diag, hits[g0 + q].apos + 1, lane);
-                  if (orig[orig[q]] == q)
-                    { if (lane == 0) E[nexp] = q;
-                      nexp += 1;
+    int chead = head[ar];
+
+    while (nidx < nhits && hits[nidx].aread == ar)
+      { const int     br = hits[nidx].bread;
+        const int64_t g0 = nidx;                         // group base: node n <-> seed g0+n
+        int *from = sc.from + g0, *orig = sc.orig + g0, *cost = sc.cost + g0, *dead = sc.dead + g0;
+        int *E = sc.E + g0;
+        int4 *S = s_S[warp];
+        NodeSm *N = s_N[warp];
+        bool spilled = false, fast = true;
+        int nn = 0, ns = 0, nexp = 0, qhead = 0;
+
+        // ---- fast path ------------------------------------------------------------------------
+        { int e_n = 0, e_d = 0, e_a = 0;                 // lane j < ns: j-th entry in key order
+          int64_t cbase = nidx;
+          int4 hv = make_int4(0, 0, -1, -1);             // (diag, apos, bread, aread) of seed cbase+lane
+          if (cbase + lane < nhits) hv = *reinterpret_cast<const int4 *>(hits + cbase + lane);
+          unsigned same = __ballot_sync(FULL, hv.w == ar && hv.z == br);
+          while (true)
+            { int off = (int) (nidx - cbase);
+              if (off == 32)
+                { cbase = nidx; off = 0;
+                  hv = make_int4(0, 0, -1, -1);
+                  if (cbase + lane < nhits) hv = *reinterpret_cast<const int4 *>(hits + cbase + lane);
+                  same = __ballot_sync(FULL, hv.w == ar && hv.z == br);
+                }
+              if (((same >> off) & 1u) == 0)             // end of the group
+                break;
+              if (ns == 32 || nn == CH_NCAP)             // hand over to the general path
+                { for (int i = lane; i < nn; i += 32)
+                    { const NodeSm x = N[i];
+                      from[i] = x.from; orig[i] = x.od & 0x7fff; cost[i] = x.cost; dead[i] = x.od >> 15;
+                    }
+                  if (lane < ns) S[lane] = make_int4(e_n, e_d, e_a, 0);
+                  __syncwarp();
+                  fast = false;
+                  break;
+                }
+              const int diag = __shfl_sync(FULL, hv.x, off);
+              const int apos = __shfl_sync(FULL, hv.y, off) + 1;
+              const int bpos = apos - diag;
+
+              while (qhead < nn)                         // map.c:1787-1796
+                { const NodeSm q = N[qhead];
+                  if (!(q.apos < apos - MAX_GAP)) break;
+                  const int qi = qhead++;
+                  if ((q.od & 0x8000) == 0)
+                    { const unsigned mt = __ballot_sync(FULL, lane < ns && e_d == q.diag && e_a == q.apos);
+                      if (mt)
+                        { const int idx = __ffs(mt) - 1;
+                          const int t_n = __shfl_down_sync(FULL, e_n, 1), t_d = __shfl_down_sync(FULL, e_d, 1);
+                          const int t_a = __shfl_down_sync(FULL, e_a, 1);
+                          if (lane >= idx) { e_n = t_n; e_d = t_d; e_a = t_a; }
+                          ns -= 1;
+                        }
+                      if ((N[q.od & 0x7fff].od & 0x7fff) == qi)
+                        { if (lane == 0) E[nexp] = qi;
+                          nexp += 1;
+                        }
                     }
                 }
-            }
 
-          const int n = nn++;
-          if (!spilled && ns + 1 > CH_SCAP)            // active set outgrew shared memory
-            { int4 *G = sc.S + g0;
-              for (int j = lane; j < ns; j += 32) G[j] = S[j];
-              __syncwarp();
-              S = G; spilled = true;
-            }
-
-          // insert position: key order diag desc, apos desc (add, map.c:1101)
-          int pos = ns;
-          for (int base = 0; base < ns; base += 32)
-            { const int j = base + lane;
-              int4 e = (j < ns) ? S[j] : make_int4(0, 0, 0, 0);
-              const unsigned b = __ballot_sync(0xffffffffu,
-                                               j < ns && (diag > e.y || (diag == e.y && apos > e.z)));
-              if (b) { pos = base + __ffs(b) - 1; break; }
-            }
-          for (int top = ns; top > pos; top -= 32)     // shift right, top chunk first
-            { const int j = top - 1 - lane;
-              int4 v = make_int4(0, 0, 0, 0);
-              if (j >= pos) v = S[j];
-              __syncwarp();
-              if (j >= pos) S[j + 1] = v;
-              __syncwarp();
-            }
-          if (lane == 0) S[pos] = make_int4(n, diag, apos, 0);
-          __syncwarp();
-          ns += 1;
-
-          // predOf + leftmost (map.c:1806-1808): nearest predecessor with bpos' >= bpos-MAX_GAP,
-          // replaced by the max-apos node on its diagonal
-          int l = -1, lj = -1, ld = 0, la = 0;
-          for (int base = pos - 1; base >= 0 && l < 0; base -= 32)
-            { const int j = base - lane;
-              int4 e = (j >= 0) ? S[j] : make_int4(0, 0, 0, 0);
-              const unsigned b = __ballot_sync(0xffffffffu, j >= 0 && (e.z - e.y) >= bpos - MAX_GAP);
-              if (b)
-                { const int src = __ffs(b) - 1;
-                  lj = base - src;
-                  l  = __shfl_sync(0xffffffffu, e.x, src);
-                  ld = __shfl_sync(0xffffffffu, e.y, src);
-                  la = __shfl_sync(0xffffffffu, e.z, src);
+              const int n = nn++;
+              int pos;                                   // insert, key order diag desc, apos desc
+              { const unsigned gt = __ballot_sync(FULL, lane < ns && (diag > e_d || (diag == e_d && apos > e_a)));
+                pos = gt ? __ffs(gt) - 1 : ns;
+                const int t_n = __shfl_up_sync(FULL, e_n, 1), t_d = __shfl_up_sync(FULL, e_d, 1);
+                const int t_a = __shfl_up_sync(FULL, e_a, 1);
+                if (lane > pos) { e_n = t_n; e_d = t_d; e_a = t_a; }
+                if (lane == pos) { e_n = n; e_d = diag; e_a = apos; }
+                ns += 1;
+              }
+              // predOf + leftmost (map.c:1806-1808), succOf (map.c:1809)
+              int l = -1, ld = 0, la = 0, r = -1, rd = 0, ra = 0;
+              { const unsigned lb = __ballot_sync(FULL, lane < pos && (e_a - e_d) >= bpos - MAX_GAP);
+                if (lb)
+                  { const int src = 31 - __clz(lb);
+                    ld = __shfl_sync(FULL, e_d, src);
+                    const unsigned eq = __ballot_sync(FULL, lane <= src && e_d == ld);
+                    const int s2 = __ffs(eq) - 1;        // equal diagonals are contiguous: first of the run
+                    l  = __shfl_sync(FULL, e_n, s2);
+                    la = __shfl_sync(FULL, e_a, s2);
+                  }
+                const unsigned rb = __ballot_sync(FULL, lane > pos && lane < ns && (e_a - e_d) <= bpos);
+                if (rb)
+                  { const int src = __ffs(rb) - 1;
+                    r  = __shfl_sync(FULL, e_n, src);
+                    rd = __shfl_sync(FULL, e_d, src);
+                    ra = __shfl_sync(FULL, e_a, src);
+                  }
+              }
+              int lcost = 0, rcost = 0;                  // map.c:1810-1826
+              if (l >= 0)
+                lcost = N[l].cost + ((apos >= la + K) ? K : apos - la);
+              if (r >= 0)
+                { const int rb_ = ra - rd;
+                  rcost = N[r].cost + ((bpos >= rb_ + K) ? K : bpos - rb_);
                 }
+              if (lcost > rcost)
+                rcost = 0;
+              else
+                lcost = 0;
+
+              if (lcost > 0 || rcost > 0)                // map.c:1828-1857
+                { const int p = (lcost > 0) ? l : r;
+                  const int c = (lcost > 0) ? lcost : rcost;
+                  const int pd = (lcost > 0) ? ld : rd, pa = (lcost > 0) ? la : ra;
+                  const NodeSm P = N[p];
+                  const int o = (P.from < 0) ? p : (P.od & 0x7fff);
+                  const unsigned short ood = N[o].od;
+                  const bool best = (c >= N[ood & 0x7fff].cost);
+                  bool drop = false;
+                  if (best)
+                    { int dd = pd - diag;
+                      if (dd < 0) dd = -dd;
+                      drop = ((double) dd <= .2 * (double) (apos - pa));
+                    }
+                  __syncwarp();
+                  if (lane == 0)
+                    { NodeSm x;
+                      x.cost = c; x.apos = apos; x.diag = diag; x.from = (short) p; x.od = (unsigned short) o;
+                      N[n] = x;
+                      if (best) N[o].od = (unsigned short) ((ood & 0x8000) | n);
+                      if (drop) N[p].od = (unsigned short) (N[p].od | 0x8000);
+                    }
+                  if (drop)
+                    { const unsigned mt = __ballot_sync(FULL, lane < ns && e_d == pd && e_a == pa);
+                      if (mt)
+                        { const int idx = __ffs(mt) - 1;
+                          const int t_n = __shfl_down_sync(FULL, e_n, 1), t_d = __shfl_down_sync(FULL, e_d, 1);
+                          const int t_a = __shfl_down_sync(FULL, e_a, 1);
+                          if (lane >= idx) { e_n = t_n; e_d = t_d; e_a = t_a; }
+                          ns -= 1;
+                        }
+                    }
+                  __syncwarp();
+                }
+              else
+                { __syncwarp();
+                  if (lane == 0)
+                    { NodeSm x;
+                      x.cost = K; x.apos = apos; x.diag = diag; x.from = -1; x.od = (unsigned short) n;
+                      N[n] = x;
+                    }
+                  __syncwarp();
+                }
+              nidx += 1;
             }
-          if (l >= 0)
-            for (int base = lj - 1; base >= 0; base -= 32)
+          if (fast)                                      // live set to shared memory for the walk below
+            { if (lane < ns) S[lane] = make_int4(e_n, e_d, e_a, 0);
+              __syncwarp();
+            }
+        }
+
+        // ---- general path (the rest of the group after a hand-over) ---------------------------
+        if (!fast)
+        for ( ; nidx < nhits; nidx++)
+          { const SeedPair hp = hits[nidx];
+            if (hp.aread != ar || hp.bread != br) break;
+            const int apos = hp.apos + 1;
+            const int diag = hp.diag;
+            const int bpos = apos - diag;
+
+            while (qhead < nn && hits[g0 + qhead].apos + 1 < apos - MAX_GAP)   // map.c:1787-1796
+              { const int q = qhead++;
+                if (!dead[q])
+                  { set_remove(S, ns, hits[g0 + q].diag, hits[g0 + q].apos + 1, lane);
+                    if (orig[orig[q]] == q)
+                      { if (lane == 0) E[nexp] = q;
+                        nexp += 1;
+                      }
+                  }
+              }
+
+            const int n = nn++;
+            if (!spilled && ns + 1 > CH_SCAP)            // active set outgrew shared memory
+              { int4 *G = sc.S + g0;
+                for (int j = lane; j < ns; j += 32) G[j] = S[j];
+                __syncwarp();
+                S = G; spilled = true;
+              }
+
+            // insert position: key order diag desc, apos desc (add, map.c:1101)
+            int pos = ns;
+            for (int base = 0; base < ns; base += 32)
+              { const int j = base + lane;
+                int4 e = (j < ns) ? S[j] : make_int4(0, 0, 0, 0);
+                const unsigned b = __ballot_sync(0xffffffffu,
+                                                 j < ns && (diag > e.y || (diag == e.y && apos > e.z)));
+                if (b) { pos = base + __ffs(b) - 1; break; }
+              }
+            for (int top = ns; top > pos; top -= 32)     // shift right, top chunk first
+              { const int j = top - 1 - lane;
+                int4 v = make_int4(0, 0, 0, 0);
+                if (j >= pos) v = S[j];
+                __syncwarp();
+                if (j >= pos) S[j + 1] = v;
+                __syncwarp();
+              }
+            if (lane == 0) S[pos] = make_int4(n, diag, apos, 0);
+            __syncwarp();
+            ns += 1;
+
+            // predOf + leftmost (map.c:1806-1808): nearest predecessor with bpos' >= bpos-MAX_GAP,
+            // replaced by the max-apos node on its diagonal
+            int l = -1, lj = -1, ld = 0, la = 0;
+            for (int base = pos - 1; base >= 0 && l < 0; base -= 32)
               { const int j = base - lane;
                 int4 e = (j >= 0) ? S[j] : make_int4(0, 0, 0, 0);
-                const unsigned b = __ballot_sync(0xffffffffu, j >= 0 && e.y == ld);
-                const int run = (b == 0xffffffffu) ? 32 : __ffs(~b) - 1;
-                if (run > 0)
-                  { l  = __shfl_sync(0xffffffffu, e.x, run - 1);
-                    la = __shfl_sync(0xffffffffu, e.z, run - 1);
+                const unsigned b = __ballot_sync(0xffffffffu, j >= 0 && (e.z - e.y) >= bpos - MAX_GAP);
+                if (b)
+                  { const int src = __ffs(b) - 1;
+                    lj = base - src;
+                    l  = __shfl_sync(0xffffffffu, e.x, src);
+                    ld = __shfl_sync(0xffffffffu, e.y, src);
+                    la = __shfl_sync(0xffffffffu, e.z, src);
                   }
-                if (run < 32) break;
               }
-          // succOf (map.c:1809): nearest successor with bpos' <= bpos
-          int r = -1, rd = 0, ra = 0;
-          for (int base = pos + 1; base < ns && r < 0; base += 32)
-            { const int j = base + lane;
-              int4 e = (j < ns) ? S[j] : make_int4(0, 0, 0, 0);
-              const unsigned b = __ballot_sync(0xffffffffu, j < ns && (e.z - e.y) <= bpos);
-              if (b)
-                { const int src = __ffs(b) - 1;
-                  r  = __shfl_sync(0xffffffffu, e.x, src);
-                  rd = __shfl_sync(0xffffffffu, e.y, src);
-                  ra = __shfl_sync(0xffffffffu, e.z, src);
+            if (l >= 0)
+              for (int base = lj - 1; base >= 0; base -= 32)
+                { const int j = base - lane;
+                  int4 e = (j >= 0) ? S[j] : make_int4(0, 0, 0, 0);
+                  const unsigned b = __ballot_sync(0xffffffffu, j >= 0 && e.y == ld);
+                  const int run = (b == 0xffffffffu) ? 32 : __ffs(~b) - 1;
+                  if (run > 0)
+                    { l  = __shfl_sync(0xffffffffu, e.x, run - 1);
+                      la = __shfl_sync(0xffffffffu, e.z, run - 1);
+                    }
+                  if (run < 32) break;
                 }
-            }
+            // succOf (map.c:1809): nearest successor with bpos' <= bpos
+            int r = -1, rd = 0, ra = 0;
+            for (int base = pos + 1; base < ns && r < 0; base += 32)
+              { const int j = base + lane;
+                int4 e = (j < ns) ? S[j] : make_int4(0, 0, 0, 0);
+                const unsigned b = __ballot_sync(0xffffffffu, j < ns && (e.z - e.y) <= bpos);
+                if (b)
+                  { const int src = __ffs(b) - 1;
+                    r  = __shfl_sync(0xffffffffu, e.x, src);
+                    rd = __shfl_sync(0xffffffffu, e.y, src);
+                    ra = __shfl_sync(0xffffffffu, e.z, src);
+                  }
+              }
 
-          int lcost = 0, rcost = 0;                   // map.c:1810-1826
-          if (l >= 0)
-            lcost = cost[l] + ((apos >= la + K) ? K : apos - la);
-          if (r >= 0)
-            { const int rb = ra - rd;
-              rcost = cost[r] + ((bpos >= rb + K) ? K : bpos - rb);
-            }
-          if (lcost > rcost)
-            rcost = 0;
-          else
-            lcost = 0;
+            int lcost = 0, rcost = 0;                   // map.c:1810-1826
+            if (l >= 0)
+              lcost = cost[l] + ((apos >= la + K) ? K : apos - la);
+            if (r >= 0)
+              { const int rb = ra - rd;
+                rcost = cost[r] + ((bpos >= rb + K) ? K : bpos - rb);
+              }
+            if (lcost > rcost)
+              rcost = 0;
+            else
+              lcost = 0;
 
-          if (lcost > 0 || rcost > 0)                 // map.c:1828-1857
-            { const int p = (lcost > 0) ? l : r;
-              const int c = (lcost > 0) ? lcost : rcost;
-              const int pd = (lcost > 0) ? ld : rd, pa = (lcost > 0) ? la : ra;
-              const int o = (from[p] < 0) ? p : orig[p];
-              const bool best = (c >= cost[orig[o]]);
-              __syncwarp();
-              if (lane == 0)
-                { from[n] = p; cost[n] = c; orig[n] = o; dead[n] = 0;
-                  if (best) orig[o] = n;
-                }
-              __syncwarp();
-              if (best)
-                { int dd = pd - diag;
-                  if (dd < 0) dd = -dd;
-                  if ((double) dd <= .2 * (double) (apos - pa))
-                    { set_remove(S, ns, pd, pa, lane);
-                      if (lane == 0) dead[p] = 1;
-                      __syncwarp();
+            if (lcost > 0 || rcost > 0)                 // map.c:1828-1857
+              { const int p = (lcost > 0) ? l : r;
+                const int c = (lcost > 0) ? lcost : rcost;
+                const int pd = (lcost > 0) ? ld : rd, pa = (lcost > 0) ? la : ra;
+                const int o = (from[p] < 0) ? p : orig[p];
+                const bool best = (c >= cost[orig[o]]);
+                __syncwarp();
+                if (lane == 0)
+                  { from[n] = p; cost[n] = c; orig[n] = o; dead[n] = 0;
+                    if (best) orig[o] = n;
+                  }
+                __syncwarp();
+                if (best)
+                  { int dd = pd - diag;
+                    if (dd < 0) dd = -dd;
+                    if ((double) dd <= .2 * (double) (apos - pa))
+                      { set_remove(S, ns, pd, pa, lane);
+                        if (lane == 0) dead[p] = 1;
+                        __syncwarp();
+                      }
+                  }
+              }
+            else
+              { if (lane == 0)
+                  { from[n] = -1; cost[n] = K; orig[n] = n; dead[n] = 0; }
+                __syncwarp();
+              }
+          }
+
+        // candidates of the group: live set in key order, then expired (newest first), map.c:1634-1767
+        __syncwarp();
+        if (lane == 0)
+          { const AccS as = { N };
+            const AccG ag = { hits, g0, from, orig, cost };
+            for (int pass = 0; pass < 2; pass++)
+              for (int jj = 0; jj < (pass == 0 ? ns : nexp); jj++)
+                { const int h = (pass == 0) ? S[jj].x : E[nexp - 1 - jj];
+                  if (fast)
+                    { if (as.cost(h) >= hithr && as.orig(as.orig(h)) == h)
+                        consider(as, h, ar, br + bstart, comp, K, profile, spacing,
+                                 cand, cand_top, cand_cap, jumps, jump_top, jump_cap, chead, cover, coff,
+                                 overflow);
+                    }
+                  else
+                    { if (cost[h] >= hithr && orig[orig[h]] == h)
+                        consider(ag, h, ar, br + bstart, comp, K, profile, spacing,
+                                 cand, cand_top, cand_cap, jumps, jump_top, jump_cap, chead, cover, coff,
+                                 overflow);
                     }
                 }
-            }
-          else
-            { if (lane == 0)
-                { from[n] = -1; cost[n] = K; orig[n] = n; dead[n] = 0; }
-              __syncwarp();
-            }
-        }
-
-      // candidates of the group: live set in key order, then expired (newest first), map.c:1634-1767
-      __syncwarp();
-      if (lane == 0)
-        { for (int pass = 0; pass < 2; pass++)
-            for (int jj = 0; jj < (pass == 0 ? ns : nexp); jj++)
-              { const int h = (pass == 0) ? S[jj].x : E[nexp - 1 - jj];
-                if (cost[h] >= hithr && orig[orig[h]] == h)
-                  consider(hits, g0, h, ar, br + bstart, comp, K, profile, spacing, from, orig, cost,
-                           cand, cand_top, cand_cap, jumps, jump_top, jump_cap, chead, cover, coff,
-                           overflow);
-              }
-        }
-      chead = __shfl_sync(0xffffffffu, chead, 0);
-      __syncwarp();
-    }
-  if (lane == 0) head[ar] = chead;
+          }
+        chead = __shfl_sync(0xffffffffu, chead, 0);
+        __syncwarp();
+      }
+    if (lane == 0) head[ar] = chead;
+  }
 }
 
 // ---- the chain kernel runs on its own stream -------------------------------------------------
@@ -431,9 +631,13 @@ void chain_seeds(Mapper *m, SeedSet *ss, int bstart, int comp, cudaStream_t stre
   const int n = m->reads->nreads;
   CUDA_CHECK(cudaEventRecord(g_ca.ready, stream));     // seeds, pools and scratch are ready
   CUDA_CHECK(cudaStreamWaitEvent(g_ca.stream, g_ca.ready, 0));
-  LAUNCH(k_chain, (n + CH_WARPS - 1) / CH_WARPS, CH_WARPS * 32, 0, g_ca.stream, ss->hits, nhits, n, g_par.kmer,
+  int *read_counter = m->cand_top + 2;                  // reads are handed out by a counter
+  CUDA_CHECK(cudaMemsetAsync(read_counter, 0, sizeof(int), g_ca.stream));
+  int grid = (n + CH_WARPS - 1) / CH_WARPS;
+  if (grid > sm_count() * CH_CTAS) grid = sm_count() * CH_CTAS;
+  LAUNCH(k_chain, grid, CH_WARPS * 32, 0, g_ca.stream, ss->hits, nhits, n, g_par.kmer,
          bstart, comp, g_par.profile, g_par.spacing, sc, m->cand, m->cand_top, m->cand_cap, m->jumps,
-         m->jump_top, (unsigned long long) m->jump_cap, m->head, m->cover, m->coff, m->overflow);
+         m->jump_top, (unsigned long long) m->jump_cap, m->head, m->cover, m->coff, m->overflow, read_counter);
   CUDA_CHECK(cudaEventRecord(g_ca.done, g_ca.stream));
   g_ca.busy = true;
   g_ca.pending.push_back(scratch);

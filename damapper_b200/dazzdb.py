@@ -190,3 +190,78 @@ def union_masks(a, b):
             pts += cur
         off.append(len(pts))
     return np.asarray(off, dtype=np.int64), np.asarray(pts, dtype=np.int32)
+
+
+class StreamDBWriter:
+    """write_db for data that does not fit in memory at once: reads are appended in chunks
+    ((bases, rlen) tuples), the stub / .idx header are written by close().  Same files as
+    write_db (reference DB.h:285-295,390-435, DB.c:319-363)."""
+
+    def __init__(self, path: str, is_dam: bool = False):
+        d, base = os.path.split(path)
+        self.d = d or "."
+        root = base
+        for ext in (".dam", ".db"):
+            if root.endswith(ext):
+                root = root[: -len(ext)]
+        self.root = root
+        self.is_dam = is_dam
+        self.stub = os.path.join(self.d, root + (".dam" if is_dam else ".db"))
+        self.bps = open(os.path.join(self.d, "." + root + ".bps"), "wb")
+        self.idx_path = os.path.join(self.d, "." + root + ".idx")
+        self.idx = open(self.idx_path, "wb")
+        self.idx.write(b"\0" * DB_HDR.size)
+        self.n = 0
+        self.boff = 0
+        self.totlen = 0
+        self.maxlen = 0
+        self.cnt = np.zeros(4, dtype=np.float64)
+
+    def append(self, bases: np.ndarray, rlen) -> None:
+        rlen = np.asarray(rlen, dtype=np.int64)
+        n = rlen.size
+        if n == 0:
+            return
+        # 2-bit pack all reads of the chunk at once: every read padded to a multiple of 4 bases
+        plen = (rlen + 3) & ~3
+        poff = np.concatenate([[0], np.cumsum(plen)])
+        soff = np.concatenate([[0], np.cumsum(rlen)])
+        padded = np.zeros(int(poff[-1]), dtype=np.uint8)
+        rid = np.repeat(np.arange(n, dtype=np.int64), rlen)
+        padded[np.arange(int(soff[-1]), dtype=np.int64) + (poff[:-1] - soff[:-1])[rid]] = bases
+        del rid
+        q = padded.reshape(-1, 4)
+        packed = ((q[:, 0] << 6) | (q[:, 1] << 4) | (q[:, 2] << 2) | q[:, 3]).astype(np.uint8)
+        self.bps.write(packed.tobytes())
+        rec = np.zeros(n, dtype=np.dtype([("origin", "<i4"), ("rlen", "<i4"), ("fpulse", "<i4"), ("p0", "<i4"),
+                                          ("boff", "<i8"), ("coff", "<i8"), ("flags", "<i4"), ("p1", "<i4")]))
+        assert rec.dtype.itemsize == DB_READ.size
+        rec["origin"] = np.arange(self.n, self.n + n)
+        rec["rlen"] = rlen
+        rec["boff"] = self.boff + poff[:-1] // 4
+        rec["flags"] = DB_BEST
+        self.idx.write(rec.tobytes())
+        self.n += n
+        self.boff += int(poff[-1]) // 4
+        self.totlen += int(soff[-1])
+        self.maxlen = max(self.maxlen, int(rlen.max()))
+        self.cnt += np.bincount(bases, minlength=4)[:4]
+
+    def close(self, nblocks: int = 1, block_bounds=None) -> str:
+        n = self.n
+        self.bps.close()
+        freq = self.cnt / max(1.0, self.cnt.sum())
+        self.idx.seek(0)
+        self.idx.write(DB_HDR.pack(n, n, 0, DB_ALL, float(freq[0]), float(freq[1]), float(freq[2]),
+                                   float(freq[3]), self.maxlen, self.totlen, n, 0, 0, 0, 0, 0, 0, 0, 0, 0))
+        self.idx.close()
+        if block_bounds is None:
+            block_bounds = [int(n * i / nblocks) for i in range(nblocks + 1)]
+        with open(self.stub, "w") as f:
+            f.write("files = %9d\n" % 1)
+            f.write("  %9d %s %s\n" % (n, self.root, self.root))
+            f.write("blocks = %9d\n" % (len(block_bounds) - 1))
+            f.write("size = %11d cutoff = %9d all = %1d\n" % (max(1, self.totlen // 1000000 + 1), 0, 1))
+            for b in block_bounds:
+                f.write(" %9d %9d\n" % (b, b))
+        return self.stub

@@ -17,6 +17,7 @@
 #include <dirent.h>
 #include <sys/stat.h>
 #include <sys/types.h>
+#include <time.h>
 #include "dazz_db.h"
 
 static const char *Prog_Name = "damapper";
@@ -27,6 +28,25 @@ static const char *Usage[] =
     "         [-e<double(.85)] [-s<int(100)>] [-n<double(1.00)>]",
     "         [-m<track>]+  <reference:dam> <reads:db> ...",
   };
+
+/* DAMGPU_TIMING=1: wall clock of every phase of the driver on stderr (development aid) */
+static int    TIMING = 0;
+static double T_last = 0., T_zero = 0.;
+
+static double now_s(void)
+{ struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC,&ts);
+  return (ts.tv_sec + 1e-9*ts.tv_nsec);
+}
+
+static void tick(const char *what)
+{ double t;
+  if (!TIMING)
+    return;
+  t = now_s();
+  fprintf(stderr,"[timing] %-28s %8.1f ms   (at %8.1f ms)\n",what,1e3*(t-T_last),1e3*(t-T_zero));
+  T_last = t;
+}
 
 static void Clean_Exit(int val)                       /* damapper.c:543-554 */
 { char command[8192];
@@ -92,6 +112,8 @@ int main(int argc, char *argv[])
   damgpu_options opts;
   damgpu_align_spec spec;
 
+  TIMING = (getenv("DAMGPU_TIMING") != NULL);
+  T_zero = T_last = now_s();
   MEM_PHYSICAL = physical_memory();
   MEM_LIMIT    = MEM_PHYSICAL;
   if (MEM_PHYSICAL == 0)
@@ -211,8 +233,10 @@ int main(int argc, char *argv[])
     MSTAT[j] = 0;
 
   /* reference: stub, block count, base frequencies (damapper.c:734-797) */
+  tick("flags");
   if (dazz_open(argv[1],&refdb) != 0)
     exit (1);
+  tick("open reference stub");
   if (refdb.part > 0)
     { fprintf(stderr,"%s: first argument '%s' cannot be a block\n",Prog_Name,argv[1]);
       exit (1);
@@ -233,6 +257,7 @@ int main(int argc, char *argv[])
         exit (1);
       }
   }
+  tick("damgpu_init");
   if (damgpu_Set_Filter_Params(KMER_LEN,MAX_REPS,NTHREADS))
     { fprintf(stderr,"Illegal combination of filter parameters\n");
       exit (1);
@@ -279,11 +304,15 @@ int main(int argc, char *argv[])
       else
         broot = strdup(bblock.root);
       dazz_view(&bblock,&bview);
+      tick("load reads block");
       if (VERBOSE)
         printf("\nBuilding index for %s\n",broot);
       dreads = damgpu_block_upload_packed(&bview,bblock.packed,bblock.poff,bblock.packed_bytes);
+      tick("upload reads block");
       bindex = damgpu_index_build(dreads);
+      tick("index reads block");
       mapper = damgpu_mapper_new(dreads,bindex);
+      tick("mapper_new");
 
       for (k = 1; k <= refdb.nblocks; k++)
         { snprintf(name,sizeof(name),"%s/%s.%d.%s",refdb.pwd,aroot,k,refdb.isdam ? "dam" : "db");
@@ -295,6 +324,7 @@ int main(int argc, char *argv[])
               if (st > 0) MSTAT[j] = 1;
             }
           dazz_view(&ablock,&aview);
+          tick("load reference block");
           if (VERBOSE)
             printf("\nBuilding index for %s.%d\n",aroot,k);
           dref = damgpu_block_upload_packed(&aview,ablock.packed,ablock.poff,ablock.packed_bytes);
@@ -314,16 +344,19 @@ int main(int argc, char *argv[])
           damgpu_index_free(aindex);
           damgpu_block_free(dref);
           dazz_close(&ablock);
+          tick("index + match, both strands");
         }
 
       snprintf(name,sizeof(name),"%s/%s.%s",refdb.pwd,aroot,refdb.isdam ? "dam" : "db");
       if (dazz_load_packed(name,&ablock) != 0)
         Clean_Exit(1);
       dazz_view(&ablock,&aview);
+      tick("load whole reference");
       if (VERBOSE)
         printf("\nFinding best matches for block %s\n",broot);
       dref = damgpu_block_upload_packed(&aview,ablock.packed,ablock.poff,ablock.packed_bytes);
       rep  = damgpu_mapper_report(mapper,dref,&spec,mflag);
+      tick("upload reference + Reporter");
       { int nfiles = 1;
         while (2*nfiles <= NTHREADS) nfiles *= 2;
         if ((mflag & 1) && damgpu_report_write_las(rep,0,SORT_PATH,broot,aroot,nfiles,SPACING))
@@ -333,6 +366,7 @@ int main(int argc, char *argv[])
         if (PROFILE && damgpu_report_write_profile(rep,&bview,".",broot,SPACING))
           Clean_Exit(1);
       }
+      tick("write .las / -p track");
       if (VERBOSE)
         { printf("      %lld mapped segments\n",(long long) damgpu_report_records(rep,(mflag & 1) ? 0 : 1));
           fflush(stdout);
@@ -344,6 +378,7 @@ int main(int argc, char *argv[])
       damgpu_index_free(bindex);
       damgpu_block_free(dreads);
       dazz_close(&bblock);
+      tick("release block");
 
       if ((mflag & 1) != 0)                              /* damapper.c:893-901 */
         { sprintf(command,"LAsort %s %s %s/%s.%s.M%c.las",VERBOSE?"-v":"",MAP_ORDER?"-a":"",
@@ -361,6 +396,7 @@ int main(int argc, char *argv[])
                           aroot,broot,SORT_PATH,aroot,broot,'@');
           SYSTEM_CHECK(command)
         }
+      tick("LAsort / LAcat / LAmerge");
       free(broot);
     }
 
