@@ -44,53 +44,55 @@ struct WaveStats { unsigned long long nwaves, ncells, nalign, empty; };
 template <int DIR> __device__ __forceinline__ bool LT(int a, int b) { return DIR > 0 ? a < b : a > b; }
 template <int DIR> __device__ __forceinline__ bool GE(int a, int b) { return DIR > 0 ? a >= b : a <= b; }
 
-// Four consecutive bases starting at byte address p, in memory order (little endian): two aligned
-// word loads and a funnel shift (the block images carry >= 16 bytes of slack at both ends).
-__device__ __forceinline__ uint32_t load4(const uint8_t *p)
-{ const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-  const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t) 3);
-  return __funnelshift_r(w[0], w[1], (unsigned) (a & 3) * 8);
+// A sequence of the 2-bit packed block image (k_pack2bit, report.cu): base x of the sequence is bit
+// pair s + x of the word stream w.  The separators of the byte image carry no information here;
+// the ends of the sequence are its length.
+struct PSeq { const uint32_t *__restrict__ w; int s, len; };
+
+// sixteen consecutive bases starting at bit pair p (any sign: the images have slack on both sides)
+__device__ __forceinline__ uint32_t win16(const uint32_t *__restrict__ w, int p)
+{ const int i = p >> 4;
+  return __funnelshift_r(__ldg(w + i), __ldg(w + i + 1), (unsigned) (p & 15) * 2);
 }
 
 // Slide along diagonal k from b-coordinate y while bases match (align.c:748-768 / 1403-1423).
-// Returns the new y; hit: 1 = ran into the end of B, 2 = into the end of A.  Four bases per
-// step: the first differing byte (xor) and the first terminator of B (bit 2 is set only in the
-// value 4) decide where and why the slide stops, exactly as the byte loop of the reference
-// (B's terminator is tested first, then the mismatch, then A's terminator).
+// Returns the new y; hit: 1 = ran into the end of B, 2 = into the end of A.  Sixteen bases per
+// step: the first differing bit pair of the xor says where the run of matches stops, the distance
+// to the nearer sequence end caps it.  The byte loop of the reference tests B's terminator first,
+// then the mismatch, then A's terminator: a run that reaches both ends together reports B's.
 template <int DIR>
-__device__ __forceinline__ int slide(const uint8_t *__restrict__ aseq, const uint8_t *__restrict__ bseq,
-                                     int k, int y, int &hit)
-{ hit = 0;
-  while (true)
-    { uint32_t wa, wb;
-      if (DIR > 0)
-        { wa = load4(aseq + k + y); wb = load4(bseq + y); }
-      else                                  // bytes y-1, y-2, .. of aseq-1+k / bseq-1 (:1017-1018)
-        { wa = __byte_perm(load4(aseq + k + y - 4), 0, 0x0123);
-          wb = __byte_perm(load4(bseq + y - 4), 0, 0x0123);
-        }
-      const uint32_t x = wa ^ wb, e = wb & 0x04040404u;
-      if ((x | e) == 0)
-        { y += 4 * DIR;
-          continue;
-        }
-      const int ix = x ? (__ffs(x) - 1) >> 3 : 4;      // first mismatch
-      const int ie = e ? (__ffs(e) - 1) >> 3 : 4;      // first terminator of B
-      if (ie <= ix)
-        { hit = 1;
-          return y + DIR * ie;
-        }
-      if (((wa >> (8 * ix)) & 0xff) == 4)
-        hit = 2;
-      return y + DIR * ix;
+__device__ __forceinline__ int slide(const PSeq &A, const PSeq &B, int k, int y, int &hit)
+{ int lim, run = 0;
+  int pa = A.s + y + k, pb = B.s + y;
+  if (DIR > 0)
+    lim = min(B.len - y, A.len - (y + k));
+  else
+    { lim = min(y, y + k);
+      pa -= 16; pb -= 16;
     }
+  while (run < lim)
+    { const uint32_t x = win16(A.w, pa) ^ win16(B.w, pb);
+      if (x != 0)
+        { run += (DIR > 0) ? ((__ffs(x) - 1) >> 1) : (__clz(x) >> 1);
+          break;
+        }
+      run += 16;
+      pa += 16 * DIR; pb += 16 * DIR;
+    }
+  if (run > lim) run = lim;
+  y += DIR * run;
+  if (DIR > 0)
+    hit = (y == B.len) ? 1 : ((y + k == A.len) ? 2 : 0);
+  else
+    hit = (y == 0) ? 1 : ((y + k == 0) ? 2 : 0);
+  return y;
 }
 
 // One forward (DIR=+1) or reverse (DIR=-1) extension from anti-diagonal mida on diagonal k0.
 // All lanes return the same value; path fields are warp-uniform.
 template <int DIR, bool DOB>
-__device__ int wave(const WaveMem &wm, const AlignSpecD &sp, const uint8_t *__restrict__ aseq,
-                    const uint8_t *__restrict__ bseq, PathD &apath, PathD &bpath, int k0, int mida,
+__device__ int wave(const WaveMem &wm, const AlignSpecD &sp, const PSeq &aseq,
+                    const PSeq &bseq, PathD &apath, PathD &bpath, int k0, int mida,
                     int aoff, int boff, int *start_diag, WaveStats &st)
 { const int lane = threadIdx.x & 31;
   const int TS = sp.spacing, PATH_AVE = sp.ave_path;
@@ -174,7 +176,8 @@ __device__ int wave(const WaveMem &wm, const AlignSpecD &sp, const uint8_t *__re
 #define CLIP_AFTER_WAVE(SETD)                                                                   \
   if (more == 0)                                                                                \
     { const int o_ = (DIR > 0) ? 0 : -1;                                                        \
-      if (bseq[besty + o_] != 4 && aseq[besta - besty + o_] != 4)                               \
+      const int yb_ = besty + o_, xa_ = besta - besty + o_;    /* neither is a terminator */     \
+      if (yb_ >= 0 && yb_ < bseq.len && xa_ >= 0 && xa_ < aseq.len)                             \
         more = 1;                                                                               \
       const bool aclipped = (DIR > 0) ? (hgh >= aclip) : (low <= aclip);                        \
       if (aclipped)                                                                             \
@@ -754,8 +757,8 @@ __device__ int wave(const WaveMem &wm, const AlignSpecD &sp, const uint8_t *__re
 // Local_Alignment as damapper calls it: (dg,dg,ad,-1,-1), reach = 1 (align.c:1727-1946).
 // DOB = false skips the B-side Pebble chain: the B path is only consumed with -C (map.c:2556-2572).
 template <bool DOB>
-__device__ int local_alignment(const WaveMem &wm, const AlignSpecD &sp, const uint8_t *aseq, int alen,
-                               const uint8_t *bseq, int blen, int acomp, int dg, int anti,
+__device__ int local_alignment(const WaveMem &wm, const AlignSpecD &sp, const PSeq &aseq, int alen,
+                               const PSeq &bseq, int blen, int acomp, int dg, int anti,
                                PathD &apath, PathD &bpath, WaveStats &st)
 { const int lane = threadIdx.x & 31;
   int aoff = 0, boff = 0, low = dg, err;
@@ -863,8 +866,11 @@ k_align(AlignArgs A)
       const Candidate cd = A.cand[job.cand];
       const int ar = job.read, br = cd.bread, cm = cd.comp;
       const int alen = A.rlen_a[ar], blen = A.rlen_b[br];
-      const uint8_t *bseq = A.bases_b + A.boff_b[br];
-      const uint8_t *aseq = (cm ? A.bases_ac : A.bases_a) + A.boff_a[ar];
+      PSeq aseq, bseq;
+      { const int64_t ob = A.boff_b[br], oa = A.boff_a[ar];
+        bseq.w = A.pk_b + (ob >> 4); bseq.s = (int) (ob & 15); bseq.len = blen;
+        aseq.w = (cm ? A.pk_ac : A.pk_a) + (oa >> 4); aseq.s = (int) (oa & 15); aseq.len = alen;
+      }
 
       int apos = cd.alast, bpos = cd.blast, alast = alen + 1;
       int first = -1, last = -1, count = 0, status = 0;

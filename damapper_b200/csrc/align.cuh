@@ -64,6 +64,7 @@ struct AlignArgs
   const Candidate *cand;
   const uint32_t  *jumps;
   const uint8_t   *bases_a, *bases_ac, *bases_b;    // reads, reverse-complemented reads, reference
+  const uint32_t  *pk_a, *pk_ac, *pk_b;             // the same images 2 bits per base (warp kernel)
   const int64_t   *boff_a, *boff_b;
   const int32_t   *rlen_a, *rlen_b;
   AlignSpecD       spec;

@@ -511,6 +511,35 @@ __global__ void __launch_bounds__(64) k_report(ReportArgs R)
     }
 }
 
+// ---- 2-bit block images for the warp alignment kernel -----------------------------------------
+// Word j of the packed image holds bytes 16j .. 16j+15 of the byte image, first base in the low
+// bits; `out` and `bases` are both the origin of the image, j runs over [first, first + nwords).
+__device__ __forceinline__ uint32_t pack4(uint32_t w)
+{ uint32_t x = w & 0x03030303u;
+  x = (x | (x >> 6)) & 0x000f000fu;
+  return (x | (x >> 12)) & 0xffu;
+}
+
+__global__ void __launch_bounds__(256)
+k_pack2bit(const uint8_t *__restrict__ bases, long long first, long long nwords, uint32_t *__restrict__ out)
+{ const long long stride = (long long) gridDim.x * blockDim.x;
+  for (long long j = first + (long long) blockIdx.x * blockDim.x + threadIdx.x; j < first + nwords; j += stride)
+    { const uint4 v = *reinterpret_cast<const uint4 *>(bases + 16 * j);
+      out[j] = pack4(v.x) | (pack4(v.y) << 8) | (pack4(v.z) << 16) | (pack4(v.w) << 24);
+    }
+}
+
+constexpr long long PK_LEAD = 8;                        // words readable before the image origin
+
+static uint32_t *pack_image(const uint8_t *bases, int64_t total, cudaStream_t stream)
+{ const long long nwords = total / 16 + 8 + PK_LEAD;    // BLOCK_SLACK covers the bytes this reads
+  uint32_t *raw = dalloc<uint32_t>((size_t) nwords + 8);
+  long long blocks = (nwords + 255) / 256;
+  if (blocks > (long long) sm_count() * 16) blocks = (long long) sm_count() * 16;
+  LAUNCH(k_pack2bit, (int) blocks, 256, 0, stream, bases, -PK_LEAD, nwords, raw + PK_LEAD);
+  return raw;
+}
+
 // ---- job enumeration ----------------------------------------------------------------------
 __global__ void k_count_cands(const int *head, const Candidate *cand, int nreads, int *cnt)
 { const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -653,6 +682,9 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   rc.raw = dalloc<uint8_t>((size_t) rd->total + 2 * BLOCK_SLACK);
   rc.bases = rc.raw + BLOCK_SLACK;
   revcomp_copy_block(rd, rc.bases, stream);
+  uint32_t *pk_a = pack_image(rd->bases, rd->total, stream);
+  uint32_t *pk_ac = pack_image(rc.bases, rd->total, stream);
+  uint32_t *pk_b = pack_image(ref->bases, ref->total, stream);
   chain_sync();                                          // the last chain call may still be running
 
   TRACE("report: spec+rc copy");
@@ -716,6 +748,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   A.jobs = d_jobs; A.job_list = nullptr; A.njobs = njobs; A.job_counter = d_ctr;
   A.cand = m->cand; A.jumps = m->jumps;
   A.bases_a = rd->bases; A.bases_ac = rc.bases; A.bases_b = ref->bases;
+  A.pk_a = pk_a + PK_LEAD; A.pk_ac = pk_ac + PK_LEAD; A.pk_b = pk_b + PK_LEAD;
   A.boff_a = rd->boff; A.boff_b = ref->boff; A.rlen_a = rd->rlen; A.rlen_b = ref->rlen;
   A.spec.spacing = S; A.spec.ave_path = ave_path; A.spec.score = d_tables; A.spec.table = d_tables + 32768;
   A.kmer = g_par.kmer; A.do_b = do_b;
@@ -904,6 +937,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   dfree(d_cells); dfree(d_tscr); dfree(d_ctr); dfree(d_ull);
   dfree(d_cell_base); dfree(d_lane_cells); dfree(d_unwind); dfree(d_lane_tscr);
   dfree(d_jobs); dfree(d_job_off); dfree(d_cnt); dfree(rc.raw); dfree(d_tables);
+  dfree(pk_a); dfree(pk_ac); dfree(pk_b);
   TRACE("report: frees");
   return out;
 }
