@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdamgpu.so")
+LIB_PATH = os.environ.get("DAMGPU_LIB") or os.path.join(HERE, "libdamgpu.so")   # DAMGPU_LIB: build variants (dev)
 
 KMER_DT = np.dtype([("code", "<u8"), ("rpos", "<i4"), ("read", "<i4")])
 SEED_DT = np.dtype([("diag", "<i4"), ("apos", "<i4"), ("bread", "<i4"), ("aread", "<i4")])

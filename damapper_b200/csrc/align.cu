@@ -336,21 +336,21 @@ __device__ int wave(const WaveMem &wm, const AlignSpecD &sp, const PSeq &aseq,
       // scan direction over the circular lane layout
       { const int cv = act ? ((DIR > 0) ? c : -c) : -IMAX;
         const int bv = (DIR > 0) ? besta : -besta;
-        // only points beyond besta can break the record; with a single one no scan is needed
-        const unsigned cand = __ballot_sync(0xffffffffu, cv > bv);
-        bool brk = (cv > bv);
-        if (cand & (cand - 1))
-          { int pm = cv;
-            for (int o = 1; o < width; o <<= 1)
-              { const int t = __shfl_sync(0xffffffffu, pm, (lane + DIR * o) & 31);
-                const bool ok = (DIR > 0) ? (k + o <= hgh) : (k - o >= low);
-                if (act && ok && t > pm) pm = t;
+        // only points beyond besta can break the record: walk them in scan order with a running
+        // maximum (there are seldom more than two or three); bit i of bm <-> diagonal base+i
+        unsigned bm = ROT(__ballot_sync(0xffffffffu, cv > bv));
+        if (bm & (bm - 1))
+          { unsigned rest = bm;
+            int rm = bv;
+            bm = 0;
+            while (rest)
+              { const int i = FIRST_SCAN(rest);
+                rest &= ~(1u << i);
+                const int t = __shfl_sync(0xffffffffu, cv, (base + i) & 31);
+                if (t > rm) { rm = t; bm |= 1u << i; }
               }
-            const int  before = __shfl_sync(0xffffffffu, pm, lp);
-            const bool hasprev = (DIR > 0) ? (k + 1 <= hgh) : (k - 1 >= low);
-            brk = brk && (!hasprev || cv > before);
           }
-        const unsigned bm = __ballot_sync(0xffffffffu, brk);
+        const bool brk = act && ((bm >> (k - base)) & 1u);
         if (bm)
           { const bool good = brk && (m >= PATH_AVE);
             bool trim = false;
@@ -362,7 +362,7 @@ __device__ int wave(const WaveMem &wm, const AlignSpecD &sp, const PSeq &aseq,
               }
             const unsigned gm = __ballot_sync(0xffffffffu, good);
             const unsigned tm = __ballot_sync(0xffffffffu, trim);
-            const int lb = (base + LAST_SCAN(ROT(bm))) & 31;
+            const int lb = (base + LAST_SCAN(bm)) & 31;
             besta = __shfl_sync(0xffffffffu, c, lb);
             besty = __shfl_sync(0xffffffffu, y, lb);
             if (gm)

@@ -23,16 +23,19 @@ struct ChainScratch                 // one slot per seed
 
 constexpr int CH_WARPS = 4;         // reads in flight per CTA
 constexpr int CH_SCAP  = 64;        // active-set entries kept in shared memory per warp (general path)
-constexpr int CH_NCAP  = 512;       // chain nodes kept in shared memory per warp (fast path)
+constexpr int CH_NCAP  = 1024;      // chain nodes kept in shared memory per warp (fast path)
 constexpr int CH_CTAS  = 6;         // CTAs per SM the shared memory allows (37 KB each)
 
-// A chain node of the fast path: everything the inner loop and the candidate walk read about a seed
-// in one 16-byte shared-memory word (the general path keeps from/orig/cost/dead in global scratch).
-struct __align__(16) NodeSm
-{ int cost, apos, diag;
+// A chain node of the fast path: one 8-byte shared-memory word (the general path keeps
+// from/orig/cost/dead in global scratch).  A group on the fast path has at most CH_NCAP nodes and a
+// node adds at most K <= 32 to the cost of its predecessor, so 16 bits hold every field.
+struct __align__(8) NodeSm
+{ unsigned short cost;
   short from;
   unsigned short od;                // orig | dead << 15
+  unsigned short pad;
 };
+static_assert(32 * CH_NCAP <= 65535 && CH_NCAP <= 0x7fff, "NodeSm fields are 16 bits");
 
 // node accessors of the two paths (same interface)
 struct AccG
@@ -45,9 +48,12 @@ struct AccG
   __device__ __forceinline__ int  cost(int n) const { return cost_[n]; }
 };
 struct AccS
-{ NodeSm *N;
-  __device__ __forceinline__ int  apos(int n) const { return N[n].apos; }
-  __device__ __forceinline__ int  bpos(int n) const { return N[n].apos - N[n].diag; }
+{ NodeSm *N; const SeedPair *hits; int64_t g0;
+  __device__ __forceinline__ int  apos(int n) const { return __ldg(&hits[g0 + n].apos) + 1; }
+  __device__ __forceinline__ int  bpos(int n) const
+  { const int2 v = __ldg(reinterpret_cast<const int2 *>(hits + g0 + n));      // (diag, apos)
+    return v.y + 1 - v.x;
+  }
   __device__ __forceinline__ int  from(int n) const { return N[n].from; }
   __device__ __forceinline__ void set_from(int n, int v) const { N[n].from = (short) v; }
   __device__ __forceinline__ int  orig(int n) const { return N[n].od & 0x7fff; }
@@ -158,7 +164,7 @@ __device__ void consider(const Acc nd, int h, int ar, int br,
 // orientation carries ~10x the seeds of one without).  A (read, contig) group starts on the FAST
 // path: the active set is one entry per lane in registers (insert / remove / predOf / leftmost /
 // succOf are a ballot and a shuffle each) and the chain nodes sit in shared memory.  When the set
-// would pass 32 entries or the group 512 nodes, the state is written out and the GENERAL path takes
+// would pass 32 entries or the group 1024 nodes, the state is written out and the GENERAL path takes
 // over for the rest of the group: sorted slice in shared memory (spilling to global scratch), nodes
 // in global scratch, the lanes scan the slice 32 entries at a time.  Both give the same result.
 __global__ void __launch_bounds__(CH_WARPS * 32)
@@ -200,6 +206,7 @@ k_chain(const SeedPair *__restrict__ hits, int64_t nhits, int nreads, int K, int
 
         // ---- fast path ------------------------------------------------------------------------
         { int e_n = 0, e_d = 0, e_a = 0;                 // lane j < ns: j-th entry in key order
+          int qd = 0, qa = 0;                            // (diag, apos) of node qhead when qhead < nn
           int64_t cbase = nidx;
           int4 hv = make_int4(0, 0, -1, -1);             // (diag, apos, bread, aread) of seed cbase+lane
           if (cbase + lane < nhits) hv = *reinterpret_cast<const int4 *>(hits + cbase + lane);
@@ -228,12 +235,16 @@ k_chain(const SeedPair *__restrict__ hits, int64_t nhits, int nreads, int K, int
               const int apos = __shfl_sync(FULL, hv.y, off) + 1;
               const int bpos = apos - diag;
 
-              while (qhead < nn)                         // map.c:1787-1796
-                { const NodeSm q = N[qhead];
-                  if (!(q.apos < apos - MAX_GAP)) break;
-                  const int qi = qhead++;
-                  if ((q.od & 0x8000) == 0)
-                    { const unsigned mt = __ballot_sync(FULL, lane < ns && e_d == q.diag && e_a == q.apos);
+              while (qhead < nn && qa < apos - MAX_GAP)  // map.c:1787-1796
+                { const int qi = qhead++;
+                  const unsigned short qod = N[qi].od;
+                  const int xd = qd, xa = qa;
+                  if (qhead < nn)                        // key of the next node to expire
+                    { const int2 v = __ldg(reinterpret_cast<const int2 *>(hits + g0 + qhead));
+                      qd = v.x; qa = v.y + 1;
+                    }
+                  if ((qod & 0x8000) == 0)
+                    { const unsigned mt = __ballot_sync(FULL, lane < ns && e_d == xd && e_a == xa);
                       if (mt)
                         { const int idx = __ffs(mt) - 1;
                           const int t_n = __shfl_down_sync(FULL, e_n, 1), t_d = __shfl_down_sync(FULL, e_d, 1);
@@ -241,12 +252,14 @@ k_chain(const SeedPair *__restrict__ hits, int64_t nhits, int nreads, int K, int
                           if (lane >= idx) { e_n = t_n; e_d = t_d; e_a = t_a; }
                           ns -= 1;
                         }
-                      if ((N[q.od & 0x7fff].od & 0x7fff) == qi)
+                      if ((N[qod & 0x7fff].od & 0x7fff) == qi)
                         { if (lane == 0) E[nexp] = qi;
                           nexp += 1;
                         }
                     }
                 }
+              if (qhead == nn)                           // the queue is empty: this seed is its head
+                { qd = diag; qa = apos; }
 
               const int n = nn++;
               int pos;                                   // insert, key order diag desc, apos desc
@@ -306,7 +319,7 @@ k_chain(const SeedPair *__restrict__ hits, int64_t nhits, int nreads, int K, int
                   __syncwarp();
                   if (lane == 0)
                     { NodeSm x;
-                      x.cost = c; x.apos = apos; x.diag = diag; x.from = (short) p; x.od = (unsigned short) o;
+                      x.cost = (unsigned short) c; x.from = (short) p; x.od = (unsigned short) o; x.pad = 0;
                       N[n] = x;
                       if (best) N[o].od = (unsigned short) ((ood & 0x8000) | n);
                       if (drop) N[p].od = (unsigned short) (N[p].od | 0x8000);
@@ -327,7 +340,7 @@ k_chain(const SeedPair *__restrict__ hits, int64_t nhits, int nreads, int K, int
                 { __syncwarp();
                   if (lane == 0)
                     { NodeSm x;
-                      x.cost = K; x.apos = apos; x.diag = diag; x.from = -1; x.od = (unsigned short) n;
+                      x.cost = (unsigned short) K; x.from = -1; x.od = (unsigned short) n; x.pad = 0;
                       N[n] = x;
                     }
                   __syncwarp();
@@ -474,7 +487,7 @@ k_chain(const SeedPair *__restrict__ hits, int64_t nhits, int nreads, int K, int
         // candidates of the group: live set in key order, then expired (newest first), map.c:1634-1767
         __syncwarp();
         if (lane == 0)
-          { const AccS as = { N };
+          { const AccS as = { N, hits, g0 };
             const AccG ag = { hits, g0, from, orig, cost };
             for (int pass = 0; pass < 2; pass++)
               for (int jj = 0; jj < (pass == 0 ? ns : nexp); jj++)
