@@ -259,10 +259,12 @@ def main():
         ig = ref_index(dref_f)
         m.match(dref_f, ig, 0, 1)
         stats["hits_fwd"] = m.last_hits
+        stats["join_fwd"] = api.last_join_times()
         ig.free()
         dref_f.complement()
         ig = ref_index(dref_f)
         m.match(dref_f, ig, 1, 0)
+        stats["join_rc"] = api.last_join_times()
         ig.free()
         dref_f.complement()                       # back to forward: Reporter wants the plain reference
         rep = m.report(dref_f, 0.85, 100, freq, 1)
@@ -295,11 +297,13 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     t0 = time.perf_counter()
-    sort_ms, sort_n, ext_ms, aln_ms = [], 0, [], []
+    sort_ms, sort_n, ext_ms, aln_ms, join_ms = [], 0, [], [], []
     for _ in range(args.steps):
         nrec, nbytes = step_resident(dr, dg)
         sort_ms.append(stats["sort"]["sort_ms"]); ext_ms.append(stats["sort"]["extract_ms"])
         aln_ms.append(stats["report"]["align_ms"])
+        join_ms.append(stats["join_fwd"]["lut_ms"] + stats["join_fwd"]["match_ms"] +
+                       stats["join_rc"]["lut_ms"] + stats["join_rc"]["match_ms"])
         sort_n = stats["sort"]["npass"]
     ev1.record()
     sync_all()
@@ -373,6 +377,17 @@ def main():
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "algorithmic_bytes_per_launch": 32 * n, "avg_launch_ms": pass_ms,
                          "launches_per_step": sort_n},
+            # merge-join of both orientations of a step: SURVEY 8(d) counts 16 B per input record per
+            # scan; here the shorter list drives and finds its codes in the longer one through a prefix
+            # table (built once per reads block), so the second call never scans the reads list
+            "roofline_merge": {"kernel": "k_build_lut + k_join_match, both orientations of a step", "bound": "hbm",
+                               "algorithmic_bytes": 2 * 16 * (stats["join_fwd"]["alen"] + stats["join_fwd"]["blen"]),
+                               "ms": float(np.mean(join_ms)),
+                               "achieved": 2 * 16.0 * (stats["join_fwd"]["alen"] + stats["join_fwd"]["blen"])
+                                           / (max(float(np.mean(join_ms)), 1e-9) / 1e3) / 1e9,
+                               "peak": peak, "unit": "GB/s",
+                               "frac": 2 * 16.0 * (stats["join_fwd"]["alen"] + stats["join_fwd"]["blen"])
+                                       / (max(float(np.mean(join_ms)), 1e-9) / 1e3) / 1e9 / peak},
             "phases_ms": {"extract": float(np.mean(ext_ms)), "radix_sort_reads": float(np.mean(sort_ms)),
                           "align_kernel": float(np.mean(aln_ms))},
             "extension": {"cells_per_s": rs["ncells"] / (max(float(np.mean(aln_ms)), 1e-9) / 1e3),

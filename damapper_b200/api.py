@@ -45,9 +45,11 @@ SYMBOLS = {
     "damgpu_set_fatal": (None, [_P]),
     "damgpu_last_error": (C.c_char_p, []),
     "damgpu_launch_count": (C.c_uint64, []),
+    "damgpu_device_memory": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "damgpu_time_kernels": (None, [C.c_int]),
     "damgpu_set_align_tier": (None, [C.c_int, C.c_int]),
     "damgpu_last_sort_times": (None, [C.POINTER(C.c_float)]),
+    "damgpu_last_join_times": (None, [C.POINTER(C.c_float)]),
     "damgpu_Set_Filter_Params": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "damgpu_Sort_Kmers": (_P, [C.POINTER(CBlock), C.POINTER(C.c_int)]),
     "damgpu_block_upload": (_P, [C.POINTER(CBlock)]),
@@ -260,6 +262,12 @@ def last_sort_times():
     v = (C.c_float * 3)()
     load().damgpu_last_sort_times(v)
     return dict(extract_ms=v[0], sort_ms=v[1], npass=int(v[2]))
+
+
+def last_join_times():
+    v = (C.c_float * 4)()
+    load().damgpu_last_join_times(v)
+    return dict(lut_ms=v[0], match_ms=v[1], alen=int(v[2]), blen=int(v[3]))
 
 
 class Report:

@@ -165,11 +165,21 @@ void damgpu_set_options(const damgpu_options *o)
 void damgpu_set_fatal(void (*clean_exit)(int)) { g_clean_exit = clean_exit; }
 const char *damgpu_last_error(void) { return g_last_error.c_str(); }
 uint64_t damgpu_launch_count(void) { return g_launches; }
+int damgpu_device_memory(uint64_t *free_bytes, uint64_t *total_bytes)
+{ need_gpu();
+  size_t f = 0, t = 0;
+  if (cudaMemGetInfo(&f, &t) != cudaSuccess)
+    return 1;
+  if (free_bytes)  *free_bytes = (uint64_t) f + g_cached_bytes;     // the allocator's cache is reusable
+  if (total_bytes) *total_bytes = (uint64_t) t;
+  return 0;
+}
 void damgpu_time_kernels(int on) { g_time_kernels = (on != 0); }
 void damgpu_set_align_tier(int tier, int slots)
 { g_align_tier = (tier < 0 || tier > 3) ? 0 : tier;
   g_align_slots = (slots == 2 || slots == 8) ? slots : 4;
 }
+void damgpu_last_join_times(float out[4]) { join_times(out); }
 void damgpu_last_sort_times(float out[3]) { out[0] = g_sort_times[0]; out[1] = g_sort_times[1]; out[2] = g_sort_times[2]; }
 
 int damgpu_Set_Filter_Params(int kmer, int suppress, int nthreads)   // map.c:124-150

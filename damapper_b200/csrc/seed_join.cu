@@ -299,6 +299,17 @@ static int compute_limit(const unsigned long long *histo, uint64_t mem_limit, in
   return j;
 }
 
+float g_join_times[4] = { 0, 0, 0, 0 };                 // lut ms, match ms, alen, blen of the last call
+static cudaEvent_t g_join_ev[3] = { nullptr, nullptr, nullptr };
+
+void join_times(float out[4])
+{ if (g_join_ev[2] != nullptr && cudaEventSynchronize(g_join_ev[2]) == cudaSuccess)
+    { cudaEventElapsedTime(&g_join_times[0], g_join_ev[0], g_join_ev[1]);
+      cudaEventElapsedTime(&g_join_times[1], g_join_ev[1], g_join_ev[2]);
+    }
+  for (int i = 0; i < 4; i++) out[i] = g_join_times[i];
+}
+
 SeedSet *merge_join(const KmerIndex *aidx, const DeviceBlock *ablock, const KmerIndex *bidx,
                     const DeviceBlock *bblock, int K, uint64_t mem_limit, cudaStream_t stream)
 { SeedSet *ss = new SeedSet();
@@ -320,6 +331,12 @@ SeedSet *merge_join(const KmerIndex *aidx, const DeviceBlock *ablock, const Kmer
   const int shift = 2 * K - P;
   const uint32_t np = 1u << P;
   uint32_t *lut;
+  cudaEvent_t *ev = g_join_ev;                           // lut | match (bench: damgpu_last_join_times)
+  if (g_time_kernels)
+    { if (ev[0] == nullptr)
+        for (int i = 0; i < 3; i++) cudaEventCreate(&ev[i]);
+      cudaEventRecord(ev[0], stream);
+    }
   if (swap && aidx->lut != nullptr)
     lut = aidx->lut;
   else
@@ -329,6 +346,7 @@ SeedSet *merge_join(const KmerIndex *aidx, const DeviceBlock *ablock, const Kmer
         aidx->lut = lut;
     }
 
+  if (g_time_kernels) cudaEventRecord(ev[1], stream);
   const uint32_t ntiles = (uint32_t) (((int64_t) dlen + JM_TILE - 1) / JM_TILE);
   uint64_t *state = dalloc<uint64_t>((size_t) ntiles + 2);
   CUDA_CHECK(cudaMemsetAsync(state, 0, sizeof(uint64_t) * ((size_t) ntiles + 2), stream));
@@ -337,6 +355,10 @@ SeedSet *merge_join(const KmerIndex *aidx, const DeviceBlock *ablock, const Kmer
   Run *runs = dalloc<Run>((size_t) dlen + 1);
   LAUNCH(k_join_match, ntiles, JM_THREADS, 0, stream, D, dlen, T, tlen, lut, shift, swap ? 1 : 0,
          runs, state, counter, counter + 1);
+  if (g_time_kernels)
+    { cudaEventRecord(ev[2], stream);                    // read by join_times(), no sync here
+      g_join_times[2] = (float) alen; g_join_times[3] = (float) blen;
+    }
   TRACE("join: lut+match launch");
   // histogram of the run products; the run count stays on the device until both are read back
   unsigned long long *gram = dalloc<unsigned long long>(MAXGRAM + 1);

@@ -17,5 +17,6 @@ struct SeedSet
 SeedSet *merge_join(const KmerIndex *aidx, const DeviceBlock *ablock, const KmerIndex *bidx,
                     const DeviceBlock *bblock, int K, uint64_t mem_limit, cudaStream_t stream);
 void     free_seeds(SeedSet *ss);
+void     join_times(float out[4]);   // ms of the prefix table build and the match kernel of the last call
 
 }  // namespace damgpu

@@ -8,7 +8,11 @@
  *
  * The reference block is uploaded once per block, indexed, matched, reverse-complemented ON
  * THE DEVICE and indexed/matched again (the reference complements on the host and re-sorts,
- * damapper.c:847-861).
+ * damapper.c:847-861).  Where the reference re-reads and re-sorts every reference block for every
+ * reads block (damapper.c:839-863), this driver keeps the two indices of a reference block -- and
+ * the whole reference the Reporter aligns against -- resident in HBM for the reads blocks that
+ * follow, as long as they fit in DAMGPU_REF_CACHE (default 45 %) of the device memory; the next
+ * reads block is read from disk by a helper thread while the GPU maps the current one.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -18,6 +22,7 @@
 #include <sys/stat.h>
 #include <sys/types.h>
 #include <time.h>
+#include <pthread.h>
 #include "dazz_db.h"
 
 static const char *Prog_Name = "damapper";
@@ -55,7 +60,9 @@ static void Clean_Exit(int val)                       /* damapper.c:543-554 */
     { fprintf(stderr,"%s: Command Failed:\n%*s      %s\n",Prog_Name,(int) strlen(Prog_Name),"",command);
       exit (1);
     }
-  exit (val);
+  tick("rm -r of the sort directory");
+  fflush(NULL);                     /* everything is on disk: leave without the CUDA runtime's */
+  _exit (val);                      /* teardown (the driver reclaims the context either way)    */
 }
 
 static uint64_t physical_memory(void)                  /* damapper.c:74-141, Linux branch */
@@ -99,6 +106,56 @@ static double arg_real(const char *arg)
      }                                                                  \
  }
 
+/* reference block k, resident between reads blocks */
+typedef struct
+  { damgpu_dblock *blk;                 /* the block (complemented: only its sizes are used again) */
+    damgpu_index  *fwd, *rev;
+    int            have;
+  } Ref_Cache;
+
+/* the next reads block, loaded by a helper thread */
+typedef struct
+  { const char *arg;
+    Dazz_Block  blk;
+    int         rc;                     /* dazz_load_packed status */
+    int         mrc[256];               /* dazz_add_mask status per -m track */
+    char      **mask;
+    int         mtop;
+    const char *prog;
+    pthread_t   th;
+    int         active;
+  } Prefetch;
+
+static void *prefetch_main(void *v)
+{ Prefetch *p = (Prefetch *) v;
+  int j;
+  p->rc = dazz_load_packed(p->arg,&p->blk);
+  if (p->rc == 0)
+    for (j = 0; j < p->mtop; j++)
+      { p->mrc[j] = dazz_add_mask(&p->blk,p->mask[j],p->prog);
+        if (p->mrc[j] < 0)
+          break;
+      }
+  return (NULL);
+}
+
+static void prefetch_start(Prefetch *p, const char *arg, char **mask, int mtop, const char *prog)
+{ memset(p,0,sizeof(*p));
+  p->arg = arg; p->mask = mask; p->mtop = mtop; p->prog = prog;
+  if (pthread_create(&p->th,NULL,prefetch_main,p) == 0)
+    p->active = 1;
+  else                                  /* no thread: load it here and now */
+    { prefetch_main(p);
+      p->active = 2;
+    }
+}
+
+static void prefetch_wait(Prefetch *p)
+{ if (p->active == 1)
+    pthread_join(p->th,NULL);
+  p->active = 0;
+}
+
 int main(int argc, char *argv[])
 { int    VERBOSE = 0, PROFILE = 0, COVER = 0, NOMAP = 0, MAP_ORDER = 1;
   int    KMER_LEN = 20, MAX_REPS = 0, NTHREADS = 4, SPACING = 100, MTOP = 0;
@@ -111,6 +168,10 @@ int main(int argc, char *argv[])
   Dazz_Block refdb, ablock, bblock;
   damgpu_options opts;
   damgpu_align_spec spec;
+  Ref_Cache *rcache;
+  damgpu_dblock *whole = NULL;                            /* whole reference, kept for the Reporter */
+  uint64_t cache_budget = 0, cache_used = 0;
+  Prefetch pre;
 
   TIMING = (getenv("DAMGPU_TIMING") != NULL);
   T_zero = T_last = now_s();
@@ -276,6 +337,17 @@ int main(int argc, char *argv[])
   damgpu_set_options(&opts);
   damgpu_set_fatal(Clean_Exit);
 
+  rcache = (Ref_Cache *) calloc((size_t) refdb.nblocks+1,sizeof(Ref_Cache));
+  { uint64_t fr = 0, tot = 0;
+    const char *e = getenv("DAMGPU_REF_CACHE");           /* percent of HBM, 0 = as the reference */
+    double pct = (e != NULL) ? atof(e) : 45.;
+    if (rcache != NULL && argc > 3 && pct > 0. && damgpu_device_memory(&fr,&tot) == 0)
+      cache_budget = (uint64_t) (tot * (pct < 90. ? pct : 90.) / 100.);
+  }
+  memset(&pre,0,sizeof(pre));
+  if (argc > 2)
+    prefetch_start(&pre,argv[2],MASK,MTOP,Prog_Name);
+
   for (i = 2; i < argc; i++)                              /* damapper.c:825-914 */
     { char *broot, *aroot = refdb.root, name[4096], command[16384];
       damgpu_block  bview, aview;
@@ -284,12 +356,13 @@ int main(int argc, char *argv[])
       damgpu_mapper *mapper;
       damgpu_report *rep;
 
-      if (dazz_load_packed(argv[i],&bblock) != 0)       /* 2 bits per base to the device */
+      prefetch_wait(&pre);                              /* 2 bits per base to the device */
+      if (pre.rc != 0)
         Clean_Exit(1);
+      bblock = pre.blk;
       for (j = 0; j < MTOP; j++)                        /* read_DB, damapper.c:352-399 */
-        { int st = dazz_add_mask(&bblock,MASK[j],Prog_Name);
-          if (st < 0) Clean_Exit(1);
-          if (st > 0) MSTAT[j] = 1;
+        { if (pre.mrc[j] < 0) Clean_Exit(1);
+          if (pre.mrc[j] > 0) MSTAT[j] = 1;
         }
       for (k = 0; k < bblock.nreads; k++)
         if (bblock.rlen[k] < KMER_LEN)
@@ -309,13 +382,26 @@ int main(int argc, char *argv[])
         printf("\nBuilding index for %s\n",broot);
       dreads = damgpu_block_upload_packed(&bview,bblock.packed,bblock.poff,bblock.packed_bytes);
       tick("upload reads block");
+      if (i+1 < argc)                                    /* the disk works while the GPU does */
+        prefetch_start(&pre,argv[i+1],MASK,MTOP,Prog_Name);
       bindex = damgpu_index_build(dreads);
       tick("index reads block");
       mapper = damgpu_mapper_new(dreads,bindex);
       tick("mapper_new");
 
       for (k = 1; k <= refdb.nblocks; k++)
-        { snprintf(name,sizeof(name),"%s/%s.%d.%s",refdb.pwd,aroot,k,refdb.isdam ? "dam" : "db");
+        { Ref_Cache *rc = rcache+k;
+          if (rc->have)                                  /* both indices are still in HBM */
+            { if (VERBOSE)
+                printf("\nComparing %s to %s.%d\n",broot,aroot,k);
+              damgpu_mapper_match(mapper,rc->blk,rc->fwd,0,(k == 1));
+              if (VERBOSE)
+                printf("\nComparing %s to c(%s.%d)\n",broot,aroot,k);
+              damgpu_mapper_match(mapper,rc->blk,rc->rev,1,0);
+              tick("match, both strands (cached)");
+              continue;
+            }
+          snprintf(name,sizeof(name),"%s/%s.%d.%s",refdb.pwd,aroot,k,refdb.isdam ? "dam" : "db");
           if (dazz_load_packed(name,&ablock) != 0)
             Clean_Exit(1);
           for (j = 0; j < MTOP; j++)
@@ -332,7 +418,15 @@ int main(int argc, char *argv[])
           if (VERBOSE)
             printf("\nComparing %s to %s.%d\n",broot,aroot,k);
           damgpu_mapper_match(mapper,dref,aindex,0,(k == 1));
-          damgpu_index_free(aindex);
+          { /* a block image + two lists of 16-byte records, one per base and strand */
+            uint64_t need = (uint64_t) ablock.totlen*33 + (uint64_t) ablock.nreads*48 + (1u << 20);
+            if (cache_budget > 0 && cache_used + need <= cache_budget)
+              { cache_used += need;
+                rc->have = 1; rc->blk = dref; rc->fwd = aindex;
+              }
+            else
+              damgpu_index_free(aindex);
+          }
 
           damgpu_block_complement(dref);
           if (VERBOSE)
@@ -341,20 +435,35 @@ int main(int argc, char *argv[])
           if (VERBOSE)
             printf("\nComparing %s to c(%s.%d)\n",broot,aroot,k);
           damgpu_mapper_match(mapper,dref,aindex,1,0);
-          damgpu_index_free(aindex);
-          damgpu_block_free(dref);
+          if (rc->have)
+            rc->rev = aindex;
+          else
+            { damgpu_index_free(aindex);
+              damgpu_block_free(dref);
+            }
           dazz_close(&ablock);
           tick("index + match, both strands");
         }
 
-      snprintf(name,sizeof(name),"%s/%s.%s",refdb.pwd,aroot,refdb.isdam ? "dam" : "db");
-      if (dazz_load_packed(name,&ablock) != 0)
-        Clean_Exit(1);
-      dazz_view(&ablock,&aview);
-      tick("load whole reference");
+      if (whole != NULL)
+        dref = whole;
+      else
+        { snprintf(name,sizeof(name),"%s/%s.%s",refdb.pwd,aroot,refdb.isdam ? "dam" : "db");
+          if (dazz_load_packed(name,&ablock) != 0)
+            Clean_Exit(1);
+          dazz_view(&ablock,&aview);
+          tick("load whole reference");
+          dref = damgpu_block_upload_packed(&aview,ablock.packed,ablock.poff,ablock.packed_bytes);
+          { uint64_t need = (uint64_t) ablock.totlen + (uint64_t) ablock.nreads*16 + (1u << 20);
+            if (cache_budget > 0 && cache_used + need <= cache_budget)
+              { cache_used += need;
+                whole = dref;
+              }
+          }
+          dazz_close(&ablock);
+        }
       if (VERBOSE)
         printf("\nFinding best matches for block %s\n",broot);
-      dref = damgpu_block_upload_packed(&aview,ablock.packed,ablock.poff,ablock.packed_bytes);
       rep  = damgpu_mapper_report(mapper,dref,&spec,mflag);
       tick("upload reference + Reporter");
       { int nfiles = 1;
@@ -372,8 +481,8 @@ int main(int argc, char *argv[])
           fflush(stdout);
         }
       damgpu_report_free(rep);
-      damgpu_block_free(dref);
-      dazz_close(&ablock);
+      if (dref != whole)
+        damgpu_block_free(dref);
       damgpu_mapper_free(mapper);
       damgpu_index_free(bindex);
       damgpu_block_free(dreads);

@@ -79,6 +79,9 @@ void damgpu_set_options(const damgpu_options *opts);
 void damgpu_set_fatal(void (*clean_exit)(int));       /* Clean_Exit, map.h:39 / damapper.c:543 */
 const char *damgpu_last_error(void);
 uint64_t damgpu_launch_count(void);                   /* kernels launched so far            */
+/* HBM of the device in use, so a driver can decide what to keep resident between blocks
+ * (the reference sizes its working set from physical memory the same way, damapper.c:74-141) */
+int  damgpu_device_memory(uint64_t *free_bytes, uint64_t *total_bytes);
 void damgpu_time_kernels(int on);                     /* record per-phase CUDA-event times  */
 /* first tier of the alignment phase: 0 = warp per candidate (default), 1 = thread per candidate,
    2 = `slots` candidates per warp with their diagonals packed onto the lanes (slots 2, 4 or 8),
@@ -87,6 +90,9 @@ void damgpu_time_kernels(int on);                     /* record per-phase CUDA-e
 void damgpu_set_align_tier(int tier, int slots);
 /* ms of the last Sort_Kmers: [0]=extraction kernel, [1]=all radix passes, [2]=#passes */
 void damgpu_last_sort_times(float out[3]);
+/* of the last merge-join (with damgpu_time_kernels on): [0]=ms of the prefix table build (0 when the
+ * cached table of the reads index was used), [1]=ms of the match kernel, [2]=alen, [3]=blen */
+void damgpu_last_join_times(float out[4]);
 
 /* ---- layer 1: the map.h quartet ------------------------------------------------------- */
 /* Set_Filter_Params, map.h:25 / map.c:124-150.  Returns 1 if kmer <= 1. */

@@ -419,3 +419,64 @@ def test_host_driver_cli(api, tmp_path):
     assert p.returncode == 1 and "Cannot specify N flag without C also" in p.stderr
     p = subprocess.run([exe, "-k33", "ref.dam", "reads.db"], cwd=wd, env=env, capture_output=True, text=True)
     assert p.returncode == 1 and "K-mer length must be 32 or less" in p.stderr
+
+
+@pytest.mark.gpu
+def test_host_driver_multiblock_reference_cache(api, tmp_path):
+    """Several reads blocks against a reference split into two blocks: the driver keeps the reference
+    indices resident between reads blocks (DAMGPU_REF_CACHE) and prefetches the next reads block; the
+    per-thread .las streams and the -p tracks must equal those of the uncached run (the reference's
+    own schedule, damapper.c:839-863) and, when the compiled reference is present, the reference's."""
+    import glob
+    import shutil
+    import subprocess
+    from damapper_b200 import dazzdb, las, synth
+    from oracle import run_ref
+    exe = os.path.join(ROOT, "damapper_b200", "damapper")
+    assert os.path.exists(exe), "host driver not built"
+    contigs, rb, rl = synth.make_config("C1", scale=0.06, seed=31)
+    wd = str(tmp_path)
+    dazzdb.write_db(os.path.join(wd, "ref.dam"), contigs, is_dam=True, nblocks=2)
+    w = dazzdb.StreamDBWriter(os.path.join(wd, "reads.db"))
+    off = np.concatenate([[0], np.cumsum(rl)])
+    half = len(rl) // 2
+    w.append(rb[:off[half]], rl[:half]); w.append(rb[off[half]:], rl[half:])
+    w.close(nblocks=3)
+    bindir = os.path.join(wd, "bin"); os.makedirs(bindir)
+    with open(os.path.join(bindir, "LAsort"), "w") as f:
+        f.write('#!/bin/bash\nfor a in "$@"; do case "$a" in -*) ;; *) pat="$a";; esac; done\n'
+                'for f in ${pat/@/[0-9]*}; do [ -e "$f" ] && cp "$f" "$DAMAPPER_KEEP_DIR"/; done\nexit 0\n')
+    for n in ("LAcat", "LAmerge"):
+        with open(os.path.join(bindir, n), "w") as f:
+            f.write("#!/bin/bash\nexit 0\n")
+    for n in ("LAsort", "LAcat", "LAmerge"):
+        os.chmod(os.path.join(bindir, n), 0o755)
+
+    def run(binary, tag, extra_env):
+        keep = os.path.join(wd, "keep_" + tag); os.makedirs(keep)
+        tmp = os.path.join(wd, "tmp_" + tag); os.makedirs(tmp)
+        env = dict(os.environ, DAMAPPER_KEEP_DIR=keep, **extra_env)
+        env["PATH"] = bindir + os.pathsep + env["PATH"]
+        p = subprocess.run([binary, "-T4", "-P" + tmp, "-C", "-p", "-M16", "ref.dam", "reads.1", "reads.2", "reads.3"],
+                           cwd=wd, env=env, capture_output=True, text=True, timeout=900)
+        assert p.returncode == 0, p.stderr
+        out = {}
+        for b in (1, 2, 3):
+            m = run_ref._thread_sorted(glob.glob(os.path.join(keep, "reads.%d.ref.M[0-9]*.las" % b)))
+            r = run_ref._thread_sorted(glob.glob(os.path.join(keep, "ref.reads.%d.R[0-9]*.las" % b)))
+            assert len(m) == 4 and len(r) == 4
+            prof = os.path.join(wd, ".reads.%d.prof.data" % b)
+            out[b] = (las.canonical_stream(m), las.canonical_stream(r), open(prof, "rb").read())
+            os.remove(prof)
+        return out, p.stderr
+
+    cached, err = run(exe, "cached", {"DAMGPU_TIMING": "1"})
+    assert "match, both strands (cached)" in err, "the reference cache was not used"
+    plain, err = run(exe, "plain", {"DAMGPU_REF_CACHE": "0", "DAMGPU_TIMING": "1"})
+    assert "(cached)" not in err
+    assert sum(len(v[0]) for v in cached.values()) > 10000
+    assert cached == plain
+    if run_ref.have_ref():
+        ref, _ = run(run_ref.REF_BIN, "ref", {})
+        assert cached == ref
+

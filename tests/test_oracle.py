@@ -175,3 +175,24 @@ def test_oracle_matches_reference_live(oracle_mod, cfg, scale, seed, flags, kw):
     out = orc.map_block(orc.HostBlock(*rd), [(orc.HostBlock(*rf), orc.HostBlock(*rc))],
                         orc.HostBlock(*rf), freq=base_freq(contigs), **kw)
     assert out["a"] == ref_a and out["b"] == ref_b and out["prof"] == ref_p
+
+
+def test_stream_db_writer_equals_write_db(tmp_path):
+    """dazzdb.StreamDBWriter (chunked appends, used for the full-size runs) writes the same stub,
+    .idx and .bps as write_db."""
+    import filecmp
+    from damapper_b200 import dazzdb, synth
+    contigs, rb, rl = synth.make_config("C1", scale=0.02, seed=3)
+    d1, d2 = str(tmp_path / "a"), str(tmp_path / "b")
+    os.makedirs(d1); os.makedirs(d2)
+    dazzdb.write_db(os.path.join(d1, "reads.db"), (rb, rl), nblocks=3)
+    w = dazzdb.StreamDBWriter(os.path.join(d2, "reads.db"))
+    off = np.concatenate([[0], np.cumsum(rl)])
+    for a, b in ((0, 7), (7, 8), (8, len(rl))):
+        w.append(rb[off[a]:off[b]], rl[a:b])
+    w.close(nblocks=3)
+    dazzdb.write_db(os.path.join(d1, "ref.dam"), contigs, is_dam=True)
+    w = dazzdb.StreamDBWriter(os.path.join(d2, "ref.dam"), is_dam=True)
+    w.append(np.concatenate(contigs), [c.size for c in contigs]); w.close()
+    for f in ("reads.db", ".reads.idx", ".reads.bps", "ref.dam", ".ref.idx", ".ref.bps"):
+        assert filecmp.cmp(os.path.join(d1, f), os.path.join(d2, f), shallow=False), f
