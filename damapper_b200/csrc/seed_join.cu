@@ -29,14 +29,33 @@ __device__ __forceinline__ void st_relaxed64(uint64_t *p, uint64_t v)
 
 // ---- prefix table over B ---------------------------------------------------------------
 // lut[p] = first index i with (B[i].code >> shift) >= p, p in [0, 2^P]; lut[2^P] = blen
-__global__ void k_build_lut(const KmerPos *__restrict__ B, int blen, int shift, uint32_t np,
-                            uint32_t *__restrict__ lut)
-{ int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > blen) return;
-  int64_t cur  = (i == blen) ? (int64_t) np : (int64_t) (B[i].code >> shift);
-  int64_t prev = (i == 0) ? -1 : (int64_t) (B[i - 1].code >> shift);
-  for (int64_t p = prev + 1; p <= cur; p++)
-    lut[p] = (uint32_t) i;
+// Four independent loads in flight per thread; the predecessor's prefix comes from the neighbouring
+// lane (lane 0 reads it).
+constexpr int LUT_UNROLL = 4;
+__global__ void __launch_bounds__(256)
+k_build_lut(const KmerPos *__restrict__ B, int blen, int shift, uint32_t np, uint32_t *__restrict__ lut)
+{ const int64_t base = ((int64_t) blockIdx.x * LUT_UNROLL) * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int64_t cur[LUT_UNROLL], prev[LUT_UNROLL];
+#pragma unroll
+  for (int u = 0; u < LUT_UNROLL; u++)
+    { const int64_t i = base + (int64_t) u * blockDim.x;
+      cur[u] = (i < blen) ? (int64_t) (__ldg(&B[i].code) >> shift) : (int64_t) np;
+    }
+#pragma unroll
+  for (int u = 0; u < LUT_UNROLL; u++)
+    { const int64_t i = base + (int64_t) u * blockDim.x;
+      prev[u] = __shfl_up_sync(0xffffffffu, cur[u], 1);
+      if (lane == 0)
+        prev[u] = (i == 0) ? -1 : ((i <= blen) ? (int64_t) (__ldg(&B[i - 1].code) >> shift) : (int64_t) np);
+    }
+#pragma unroll
+  for (int u = 0; u < LUT_UNROLL; u++)
+    { const int64_t i = base + (int64_t) u * blockDim.x;
+      if (i <= blen)
+        for (int64_t p = prev[u] + 1; p <= cur[u]; p++)
+          lut[p] = (uint32_t) i;
+    }
 }
 
 // end of the run of code c that starts at `s` (galloping, runs can be long on repeats)
@@ -341,7 +360,7 @@ SeedSet *merge_join(const KmerIndex *aidx, const DeviceBlock *ablock, const Kmer
     lut = aidx->lut;
   else
     { lut = dalloc<uint32_t>((size_t) np + 2);
-      LAUNCH(k_build_lut, (tlen + 256) / 256, 256, 0, stream, T, tlen, shift, np, lut);
+      LAUNCH(k_build_lut, (tlen + 256 * LUT_UNROLL) / (256 * LUT_UNROLL), 256, 0, stream, T, tlen, shift, np, lut);
       if (swap)
         aidx->lut = lut;
     }

@@ -452,12 +452,12 @@ def test_host_driver_multiblock_reference_cache(api, tmp_path):
     for n in ("LAsort", "LAcat", "LAmerge"):
         os.chmod(os.path.join(bindir, n), 0o755)
 
-    def run(binary, tag, extra_env):
+    def run(binary, tag, extra_env, flags):
         keep = os.path.join(wd, "keep_" + tag); os.makedirs(keep)
         tmp = os.path.join(wd, "tmp_" + tag); os.makedirs(tmp)
         env = dict(os.environ, DAMAPPER_KEEP_DIR=keep, **extra_env)
         env["PATH"] = bindir + os.pathsep + env["PATH"]
-        p = subprocess.run([binary, "-T4", "-P" + tmp, "-C", "-p", "-M16", "ref.dam", "reads.1", "reads.2", "reads.3"],
+        p = subprocess.run([binary, "-T4", "-P" + tmp, "-M16"] + flags + ["ref.dam", "reads.1", "reads.2", "reads.3"],
                            cwd=wd, env=env, capture_output=True, text=True, timeout=900)
         assert p.returncode == 0, p.stderr
         out = {}
@@ -466,17 +466,26 @@ def test_host_driver_multiblock_reference_cache(api, tmp_path):
             r = run_ref._thread_sorted(glob.glob(os.path.join(keep, "ref.reads.%d.R[0-9]*.las" % b)))
             assert len(m) == 4 and len(r) == 4
             prof = os.path.join(wd, ".reads.%d.prof.data" % b)
-            out[b] = (las.canonical_stream(m), las.canonical_stream(r), open(prof, "rb").read())
-            os.remove(prof)
+            pdata = b""
+            if "-p" in flags:
+                pdata = open(prof, "rb").read()
+                os.remove(prof)
+            out[b] = (las.canonical_stream(m), las.canonical_stream(r), pdata)
         return out, p.stderr
 
-    cached, err = run(exe, "cached", {"DAMGPU_TIMING": "1"})
+    cached, err = run(exe, "cached", {"DAMGPU_TIMING": "1"}, ["-C"])
     assert "match, both strands (cached)" in err, "the reference cache was not used"
-    plain, err = run(exe, "plain", {"DAMGPU_REF_CACHE": "0", "DAMGPU_TIMING": "1"})
+    plain, err = run(exe, "plain", {"DAMGPU_REF_CACHE": "0", "DAMGPU_TIMING": "1"}, ["-C"])
     assert "(cached)" not in err
     assert sum(len(v[0]) for v in cached.values()) > 10000
     assert cached == plain
     if run_ref.have_ref():
-        ref, _ = run(run_ref.REF_BIN, "ref", {})
+        ref, _ = run(run_ref.REF_BIN, "ref", {}, ["-C"])
         assert cached == ref
+    # with -p as well (the unmodified reference segfaults on -p with a reference of two blocks and
+    # several reads blocks, so this half has no third arm)
+    cached, _ = run(exe, "cached_p", {}, ["-C", "-p"])
+    plain, _ = run(exe, "plain_p", {"DAMGPU_REF_CACHE": "0"}, ["-C", "-p"])
+    assert all(len(v[2]) > 0 for v in cached.values())
+    assert cached == plain
 
