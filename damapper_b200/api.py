@@ -58,6 +58,10 @@ SYMBOLS = {
     "damgpu_block_complement": (None, [_P]),
     "damgpu_block_download_bases": (None, [_P, _P]),
     "damgpu_index_build": (_P, [_P]),
+    "damgpu_index_build_deferred": (_P, [_P]),
+    "damgpu_index_is_deferred": (C.c_int, [_P]),
+    "damgpu_set_reads_filter": (None, [C.c_int, C.c_int]),
+    "damgpu_last_filter_times": (None, [C.POINTER(C.c_float)]),
     "damgpu_index_len": (C.c_int, [_P]),
     "damgpu_index_download": (None, [_P, _P]),
     "damgpu_index_free": (None, [_P]),
@@ -202,8 +206,22 @@ class DeviceBlock:
 
 
 class Index:
-    def __init__(self, blk: DeviceBlock = None, handle=None):
-        self.h = handle if handle is not None else load().damgpu_index_build(blk.h)
+    """Sort_Kmers of a resident block.  deferred=True is the reads-side form: the list is built
+    (filtered by the reference block's codes) by the first Match_Filter that uses it; the block must
+    stay alive as long as the index."""
+
+    def __init__(self, blk: DeviceBlock = None, handle=None, deferred: bool = False):
+        if handle is not None:
+            self.h = handle
+        elif deferred:
+            self.h = load().damgpu_index_build_deferred(blk.h)
+            self._blk = blk
+        else:
+            self.h = load().damgpu_index_build(blk.h)
+
+    @property
+    def is_deferred(self) -> bool:
+        return bool(load().damgpu_index_is_deferred(self.h))
 
     def __len__(self):
         return load().damgpu_index_len(self.h)
@@ -268,6 +286,20 @@ def last_join_times():
     v = (C.c_float * 4)()
     load().damgpu_last_join_times(v)
     return dict(lut_ms=v[0], match_ms=v[1], alen=int(v[2]), blen=int(v[3]))
+
+
+def last_filter_times():
+    """Of the last filtered build of a deferred reads index (kernel timing on): ms of the reference
+    bitmap, of the filtered extraction, of the radix passes over the survivors; survivors."""
+    v = (C.c_float * 4)()
+    load().damgpu_last_filter_times(v)
+    return dict(bitmap_ms=v[0], extract_ms=v[1], sort_ms=v[2], survivors=int(v[3]))
+
+
+def set_reads_filter(mode: str = "auto", log2_bits: int = 0):
+    """off: a deferred reads index is simply sorted; auto: filtered when the block is large;
+    always: filtered whatever the size (parity tests)."""
+    load().damgpu_set_reads_filter({"off": 0, "auto": 1, "always": 2}[mode], log2_bits)
 
 
 class Report:
@@ -365,7 +397,8 @@ class Mapper:
 
 def map_block(reads: HostBlock, ref_blocks, wholeref: HostBlock, kmer=20, suppress=0, spacing=100,
               profile=0, ave_corr=0.85, best_tie=1.0, freq=(.25, .25, .25, .25),
-              mem_limit=64 << 30, do_a=1, do_b=0, nthreads=4, want_candidates=False):
+              mem_limit=64 << 30, do_a=1, do_b=0, nthreads=4, want_candidates=False,
+              reads_filter="auto"):
     """The damapper flow for one reads block (damapper.c:825-879) on the GPU: index the reads,
     then for every reference block Match_Filter forward and complemented (the block is
     complemented on the device), then Reporter against the whole reference.
@@ -373,8 +406,9 @@ def map_block(reads: HostBlock, ref_blocks, wholeref: HostBlock, kmer=20, suppre
     init()
     set_filter_params(kmer, suppress, nthreads)
     set_options(profile=profile, spacing=spacing, best_tie=best_tie, mem_limit=mem_limit)
+    set_reads_filter(reads_filter)
     dr = DeviceBlock(reads)
-    ir = Index(dr)
+    ir = Index(dr, deferred=True)         # the reads list is built per reference block (kmer_filter.cu)
     m = Mapper(dr, ir)
     for k, fwd in enumerate(ref_blocks):
         dg = DeviceBlock(fwd)
@@ -393,4 +427,5 @@ def map_block(reads: HostBlock, ref_blocks, wholeref: HostBlock, kmer=20, suppre
     out = dict(a=rep.a, anrec=rep.records(0), b=rep.b, bnrec=rep.records(1), prof=rep.prof,
                stats=rep.stats(), candidates=cands, cover=cover)
     rep.free(); dw.free(); m.free(); ir.free(); dr.free()
+    set_reads_filter("auto")
     return out

@@ -26,6 +26,7 @@ static float       g_sort_times[3] = { 0, 0, 0 };
 
 Params g_par;          // filter parameters + the map.h globals
 bool   g_trace = false;
+bool   g_debug_sync = false;
 int    g_align_tier = 0, g_align_slots = 4;
 bool   g_chain_async = true;
 
@@ -147,11 +148,16 @@ int damgpu_init(int device)
     }
   g_sms = prop.multiProcessorCount;
   g_trace = (getenv("DAMGPU_TRACE") != nullptr);
+  g_debug_sync = (getenv("DAMGPU_DEBUG_SYNC") != nullptr);
   if (const char *t = getenv("DAMGPU_ALIGN"))
     g_align_tier = !strcmp(t, "warp") ? 0 : !strcmp(t, "lane") ? 1 : !strcmp(t, "group") ? 3 : 2;
   g_chain_async = (getenv("DAMGPU_SYNC_CHAIN") == nullptr);
   if (const char *t = getenv("DAMGPU_SLOTS"))
     g_align_slots = atoi(t);
+  if (const char *t = getenv("DAMGPU_FILTER"))
+    g_filter_mode = !strcmp(t, "off") ? 0 : !strcmp(t, "always") ? 2 : 1;
+  if (const char *t = getenv("DAMGPU_FILTER_BITS"))
+    g_filter_log2 = (atoi(t) >= 10 && atoi(t) <= 32) ? atoi(t) : 0;
   g_ready = true;
   return 0;
 }
@@ -232,11 +238,34 @@ damgpu_index *damgpu_index_build(const damgpu_dblock *blk)
   return reinterpret_cast<damgpu_index *>(idx);
 }
 
+/* Sort_Kmers for the reads side of Match_Filter, list left unbuilt (kmer_filter.cu) */
+damgpu_index *damgpu_index_build_deferred(const damgpu_dblock *blk)
+{ need_gpu();
+  if (g_par.kmer <= 1)
+    fatal("Sort_Kmers called before Set_Filter_Params");
+  KmerIndex *idx = sort_kmers_deferred(reinterpret_cast<const DeviceBlock *>(blk), g_par.kmer,
+                                       g_par.suppress, 0);
+  g_sort_times[0] = idx->ms_extract; g_sort_times[1] = idx->ms_sort; g_sort_times[2] = (float) idx->npass;
+  return reinterpret_cast<damgpu_index *>(idx);
+}
+
+int damgpu_index_is_deferred(const damgpu_index *idx)
+{ return idx != nullptr && reinterpret_cast<const KmerIndex *>(idx)->deferred; }
+
+void damgpu_set_reads_filter(int mode, int log2_bits)
+{ g_filter_mode = (mode < 0 || mode > 2) ? 1 : mode;
+  g_filter_log2 = (log2_bits < 10 || log2_bits > 32) ? 0 : log2_bits;
+}
+
+void damgpu_last_filter_times(float out[4])
+{ for (int i = 0; i < 4; i++) out[i] = g_filter_times[i]; }
+
 int damgpu_index_len(const damgpu_index *idx)
 { return idx ? reinterpret_cast<const KmerIndex *>(idx)->len : 0; }
 
 void damgpu_index_download(const damgpu_index *i, damgpu_kmer *out)
 { const KmerIndex *idx = reinterpret_cast<const KmerIndex *>(i);
+  materialize_index(const_cast<KmerIndex *>(idx), 0);
   if (idx->len > 0)
     CUDA_CHECK(cudaMemcpy(out, idx->list, sizeof(KmerPos) * ((size_t) idx->len + 2),
                           cudaMemcpyDeviceToHost));
@@ -245,10 +274,13 @@ void damgpu_index_download(const damgpu_index *i, damgpu_kmer *out)
 void damgpu_index_free(damgpu_index *idx) { free_index(reinterpret_cast<KmerIndex *>(idx)); }
 
 void *damgpu_index_device_ptr(const damgpu_index *idx)
-{ return reinterpret_cast<const KmerIndex *>(idx)->list; }
+{ materialize_index(const_cast<KmerIndex *>(reinterpret_cast<const KmerIndex *>(idx)), 0);
+  return reinterpret_cast<const KmerIndex *>(idx)->list;
+}
 
 void damgpu_index_export(const damgpu_index *i, void *dst)
 { const KmerIndex *idx = reinterpret_cast<const KmerIndex *>(i);
+  materialize_index(const_cast<KmerIndex *>(idx), 0);
   if (idx->len > 0)
     CUDA_CHECK(cudaMemcpy(dst, idx->list, sizeof(KmerPos) * ((size_t) idx->len + 2),
                           cudaMemcpyDeviceToDevice));
@@ -496,7 +528,8 @@ static const void *g_mapper_key = nullptr;
 void *damgpu_Sort_Kmers(const damgpu_block *block, int *len)
 { need_gpu();
   DeviceBlock *blk = upload(block);
-  KmerIndex *idx = reinterpret_cast<KmerIndex *>(damgpu_index_build(reinterpret_cast<damgpu_dblock *>(blk)));
+  // reads or reference block is not known yet: deferred, Match_Filter builds what it needs
+  KmerIndex *idx = reinterpret_cast<KmerIndex *>(damgpu_index_build_deferred(reinterpret_cast<damgpu_dblock *>(blk)));
   *len = idx->len;
   if (idx->len == 0)
     { free_index(idx);

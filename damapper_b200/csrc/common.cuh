@@ -27,10 +27,16 @@ void fatal(const char *fmt, ...);
 
 // Counts kernel launches issued by the library (bench.py reports it as gpu_launches).
 extern unsigned long long g_launches;
+extern bool g_debug_sync;          // DAMGPU_DEBUG_SYNC=1: synchronise and check after every launch
 #define LAUNCH(kernel, grid, block, smem, stream, ...)                \
   do { kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);    \
        damgpu::g_launches += 1;                                       \
        KERNEL_CHECK();                                                \
+       if (damgpu::g_debug_sync)                                      \
+         { cudaError_t e_ = cudaDeviceSynchronize();                  \
+           if (e_ != cudaSuccess)                                     \
+             damgpu::fatal("kernel %s failed: %s (%s:%d)", #kernel, cudaGetErrorString(e_), __FILE__, __LINE__); \
+         }                                                            \
   } while (0)
 
 // Device memory comes from a caching allocator owned by the library (capi.cu): freed blocks go

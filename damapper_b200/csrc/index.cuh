@@ -32,6 +32,15 @@ struct KmerIndex
   DeviceBlock *block = nullptr;   // block the list was built from, owned when set (layer 1)
   mutable uint32_t *lut = nullptr;   // prefix table over the code, built by the first merge-join that
                                   // searches this list (seed_join.cu), released with the index
+  int      limit_len = -1;        // filtered view: the length of the whole list (`alen` of the hit cap,
+                                  // map.c:3002-3007); -1 = len
+  // deferred reads index (kmer_filter.cu): list == nullptr, len = the count, until something needs it
+  bool     deferred = false;
+  const DeviceBlock *src = nullptr;  // block to extract from (must outlive the index)
+  int      K = 0;
+  KmerIndex *filt = nullptr;      // sub-list of the records whose code occurs in one reference block
+  unsigned long long filt_sig = 0;   // orientation-invariant signature of that reference list
+  int      filt_blen = 0, nfilt = 0;
 };
 
 DeviceBlock *upload_block(const uint8_t *bases, const int64_t *boff, const int32_t *rlen,
@@ -51,5 +60,12 @@ void         complement_block(DeviceBlock *blk, cudaStream_t stream);
 void         revcomp_copy_block(const DeviceBlock *blk, uint8_t *dst_bases, cudaStream_t stream);
 KmerIndex   *sort_kmers(const DeviceBlock *blk, int K, int suppress, cudaStream_t stream);
 void         free_index(KmerIndex *idx);
+// kmer_filter.cu: Sort_Kmers of a reads block with the list left unbuilt; the list the merge-join of
+// reads index a against reference index b runs on (a, or its filtered view); build the whole list
+KmerIndex   *sort_kmers_deferred(const DeviceBlock *blk, int K, int suppress, cudaStream_t stream);
+const KmerIndex *reads_view(const KmerIndex *a, const KmerIndex *b, cudaStream_t stream);
+void         materialize_index(KmerIndex *idx, cudaStream_t stream);
+extern int   g_filter_mode, g_filter_log2;
+extern float g_filter_times[4];
 
 }  // namespace damgpu

@@ -546,6 +546,7 @@ void free_index(KmerIndex *idx)
 { if (idx == nullptr) return;
   dfree(idx->list);
   dfree(idx->lut);
+  free_index(idx->filt);
   free_block(idx->block);
   delete idx;
 }

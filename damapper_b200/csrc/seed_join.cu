@@ -332,9 +332,24 @@ void join_times(float out[4])
 SeedSet *merge_join(const KmerIndex *aidx, const DeviceBlock *ablock, const KmerIndex *bidx,
                     const DeviceBlock *bblock, int K, uint64_t mem_limit, cudaStream_t stream)
 { SeedSet *ss = new SeedSet();
-  const int alen = aidx->len, blen = bidx->len;
-  if (alen == 0 || blen == 0)
+  if (aidx->len == 0 || bidx->len == 0)
     return ss;
+  if (bidx->deferred)
+    materialize_index(const_cast<KmerIndex *>(bidx), stream);
+  const int full_alen = aidx->len;                     // `alen` of the hit cap: the whole reads list
+  aidx = reads_view(aidx, bidx, stream);               // deferred reads index: its filtered view
+  const int alen = aidx->len, blen = bidx->len;
+  if (alen == 0)                                       // no reads k-mer occurs in the reference block
+    { ss->histo.assign(MAXGRAM + 1, 0);
+      ss->limit = compute_limit(ss->histo.data(), mem_limit, ablock->sizeof_db, bblock->sizeof_db,
+                                full_alen, blen);
+      if (mem_limit > 0 && ss->limit <= 1)               // map.c:3017-3028
+        fatal("Insufficient memory allocation (%.1fGb), reduce block size or increase allocation",
+              (1. * mem_limit) / 0x40000000ll);
+      ss->hits = dalloc<SeedPair>(1);
+      LAUNCH(k_seed_sentinel, 1, 1, 0, stream, ss->hits, (uint64_t) 0);
+      return ss;
+    }
   const KmerPos *A = aidx->list, *B = bidx->list;
 
   TRACE(nullptr);
@@ -398,7 +413,7 @@ SeedSet *merge_join(const KmerIndex *aidx, const DeviceBlock *ablock, const Kmer
 
   TRACE("join: match sync+histogram");
   const int limit = compute_limit(ss->histo.data(), mem_limit, ablock->sizeof_db,
-                                  bblock->sizeof_db, alen, blen);
+                                  bblock->sizeof_db, full_alen, blen);
   ss->limit = limit;
   if (mem_limit > 0 && limit <= 1)                     // map.c:3017-3028
     fatal("Insufficient memory allocation (%.1fGb), reduce block size or increase allocation",

@@ -384,7 +384,9 @@ int main(int argc, char *argv[])
       tick("upload reads block");
       if (i+1 < argc)                                    /* the disk works while the GPU does */
         prefetch_start(&pre,argv[i+1],MASK,MTOP,Prog_Name);
-      bindex = damgpu_index_build(dreads);
+      /* one or two reference blocks: the reads list is built per block from the k-mers that occur in
+         it (deferred); more: sorted once in full */
+      bindex = (refdb.nblocks <= 2) ? damgpu_index_build_deferred(dreads) : damgpu_index_build(dreads);
       tick("index reads block");
       mapper = damgpu_mapper_new(dreads,bindex);
       tick("mapper_new");

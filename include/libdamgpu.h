@@ -123,6 +123,25 @@ void           damgpu_block_complement(damgpu_dblock *blk);
 void           damgpu_block_download_bases(const damgpu_dblock *blk, uint8_t *bases);
 
 damgpu_index  *damgpu_index_build(const damgpu_dblock *blk);               /* Sort_Kmers */
+/* Sort_Kmers for the READS side of Match_Filter, deferred: Match_Filter uses the reads list only
+ * through the merge-join with one reference block's list (map.c:881-1002), where a record whose code
+ * does not occur in the reference list contributes nothing.  The call records the block (which must
+ * outlive the index); the first damgpu_mapper_match / damgpu_seeds_build / damgpu_Match_Filter
+ * against a reference list extracts again with a membership test (hash bitmap of the reference codes
+ * in both orientations), compacts in extraction order and sorts the survivors -- a sub-list of the
+ * reference's sorted list holding every record that can match, so run pairs, `gram` histogram and
+ * seeds are identical.  The filtered list is reused for the complemented block.  With -t or masks, on
+ * small blocks, or when the whole list is asked for (download / export / device_ptr, a third
+ * reference block) the full list is built as by damgpu_index_build.  damgpu_index_len is the full
+ * count either way. */
+damgpu_index  *damgpu_index_build_deferred(const damgpu_dblock *blk);
+int            damgpu_index_is_deferred(const damgpu_index *idx);
+/* mode 0 = never filter, 1 = automatic (default), 2 = always; log2_bits = size of the bitmap
+ * (0 = 32 bits per reference k-mer).  Environment: DAMGPU_FILTER=off|auto|always, DAMGPU_FILTER_BITS */
+void           damgpu_set_reads_filter(int mode, int log2_bits);
+/* [0]=ms bitmap, [1]=ms filtered extraction, [2]=ms radix passes, [3]=survivors of the last filtered
+ * build (with damgpu_time_kernels on) */
+void           damgpu_last_filter_times(float out[4]);
 int            damgpu_index_len(const damgpu_index *idx);
 void           damgpu_index_download(const damgpu_index *idx, damgpu_kmer *out); /* len+2 recs */
 void           damgpu_index_free(damgpu_index *idx);

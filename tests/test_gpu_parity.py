@@ -20,13 +20,13 @@ def api():
     return a
 
 
-def _gpu_vs_oracle(api, orc, cfg, scale, seed, **kw):
+def _gpu_vs_oracle(api, orc, cfg, scale, seed, reads_filter="auto", **kw):
     contigs, rb, rl, rd, rf, rc = make_case(cfg, scale, seed)
     freq = base_freq(contigs)
     o = orc.map_block(orc.HostBlock(*rd), [(orc.HostBlock(*rf), orc.HostBlock(*rc))],
                       orc.HostBlock(*rf), freq=freq, **kw)
     g = api.map_block(api.HostBlock(*rd), [api.HostBlock(*rf)], api.HostBlock(*rf), freq=freq,
-                      want_candidates=True, **kw)
+                      want_candidates=True, reads_filter=reads_filter, **kw)
     oc, ojc, oj = o["candidates"]
     gc, gjc, gj = g["candidates"]
     assert oc.tobytes() == gc.tobytes(), "candidate chains differ"
@@ -126,6 +126,96 @@ def test_index_and_seeds_match_oracle(api, oracle_mod, cfg, scale, seed, kmer, s
     # complemented index too
     igc = api.Index(dg)
     assert igc.download().tobytes() == orc.sort_kmers(orc.HostBlock(*rc), kmer, suppress).tobytes()
+
+
+@pytest.mark.parametrize("cfg,scale,seed,kmer,bits", [
+    ("C1", 0.1, 51, 20, 0), ("C3", 0.004, 52, 14, 0), ("C5", 0.1, 53, 32, 0), ("C1", 0.05, 54, 12, 0),
+    ("C1", 0.1, 55, 20, 12),      # a 4096-bit bitmap: nearly every k-mer is a false positive
+])
+def test_deferred_reads_index(api, oracle_mod, cfg, scale, seed, kmer, bits):
+    """The reads-side Sort_Kmers left unbuilt: Match_Filter's merge-join runs on the sub-list of the
+    records whose code occurs in the reference block (either orientation) and yields the same
+    histogram, cap and seed array as the full list; asking for the list builds all of it."""
+    orc = oracle_mod
+    contigs, rb, rl, rd, rf, rc = make_case(cfg, scale, seed)
+    api.set_filter_params(kmer, 0, 4)
+    api.set_options()
+    api.set_reads_filter("always", bits)
+    try:
+        hr, hg = api.HostBlock(*rd), api.HostBlock(*rf)
+        dr, dg = api.DeviceBlock(hr), api.DeviceBlock(hg)
+        ir = api.Index(dr, deferred=True)
+        o_r = orc.sort_kmers(orc.HostBlock(*rd), kmer, 0)
+        assert ir.is_deferred and len(ir) == o_r.size - 2
+        for comp, ohb in ((0, rf), (1, rc)):
+            ig = api.Index(dg)
+            s = api.Seeds(ir, dr, ig, dg)
+            o_g = orc.sort_kmers(orc.HostBlock(*ohb), kmer, 0)
+            os_, nh, lim, histo = orc.merge_join(o_r, o_g, 64 << 30, hr.sizeof_db, hg.sizeof_db,
+                                                 hr.maxlen, hr.nreads, hg.nreads)
+            assert s.count == nh and s.limit == lim
+            assert (s.histogram() == histo).all()
+            assert s.download().tobytes() == os_.tobytes()
+            if comp == 0:
+                survivors = api.last_filter_times()["survivors"]
+                assert 0 < survivors <= o_r.size - 2
+                if bits == 0:
+                    assert survivors < (o_r.size - 2) // 2
+            s.free(); ig.free()
+            dg.complement()
+        assert ir.is_deferred                              # both orientations ran on the filtered list
+        assert ir.download().tobytes() == o_r.tobytes()    # the whole list on demand
+        assert not ir.is_deferred
+    finally:
+        api.set_reads_filter("auto")
+
+
+@pytest.mark.parametrize("cfg,scale,seed,kw", [
+    ("C1", 0.1, 56, dict(do_b=1, profile=1)),
+    ("C3", 0.01, 57, dict(profile=1, best_tie=0.95)),
+    ("C5", 0.2, 58, dict(do_b=1, best_tie=0.8, kmer=16)),
+    ("C1", 0.05, 59, dict(mem_limit=0)),
+])
+def test_pipeline_with_filtered_reads_index(api, oracle_mod, cfg, scale, seed, kw):
+    """Whole path with the filtered reads list forced on small inputs: candidates, records, -p."""
+    _gpu_vs_oracle(api, oracle_mod, cfg, scale, seed, reads_filter="always", **kw)
+
+
+def test_filtered_reads_index_over_reference_blocks(api, oracle_mod):
+    """Three reference blocks: a filtered list per block (signature changes), results as the oracle's;
+    a reads block without any k-mer of the reference gives no seeds."""
+    orc = oracle_mod
+    contigs, rb, rl, rd, rf, rc = make_case("C1", 0.12, 60)
+    from damapper_b200 import dazzdb
+    freq = base_freq(contigs)
+    g = np.concatenate(contigs)
+    cut = [0, g.size // 3, 2 * g.size // 3, g.size]
+    parts = [[g[cut[i]:cut[i + 1]]] for i in range(3)]
+    fwd, pairs, first = [], [], 0
+    for p in parts:
+        f, c = dazzdb.load_block(p), dazzdb.load_block(dazzdb.revcomp_contigs(p))
+        fwd.append(api.HostBlock(*f, tfirst=first))
+        pairs.append((orc.HostBlock(*f, tfirst=first), orc.HostBlock(*c, tfirst=first)))
+        first += 1
+    whole = dazzdb.load_block([p[0] for p in parts])
+    o = orc.map_block(orc.HostBlock(*rd), pairs, orc.HostBlock(*whole), freq=freq, do_b=1)
+    for mode in ("always", "auto", "off"):
+        out = api.map_block(api.HostBlock(*rd), fwd, api.HostBlock(*whole), freq=freq, do_b=1,
+                            reads_filter=mode)
+        assert out["a"] == o["a"] and out["b"] == o["b"], mode
+    # reads that share nothing with the reference (poly-A reads against a poly-C contig)
+    api.set_filter_params(20, 0, 4)
+    api.set_options()
+    api.set_reads_filter("always")
+    try:
+        ra = dazzdb.load_block((np.zeros(4000, dtype=np.uint8), np.array([2000, 2000], dtype=np.int32)))
+        gc_ = dazzdb.load_block([np.ones(3000, dtype=np.uint8)])
+        dr, dg = api.DeviceBlock(api.HostBlock(*ra)), api.DeviceBlock(api.HostBlock(*gc_))
+        ir, ig = api.Index(dr, deferred=True), api.Index(dg)
+        s = api.Seeds(ir, dr, ig, dg)
+        assert s.count == 0 and s.limit == 10000
+    finally:
+        api.set_reads_filter("auto")
 
 
 def test_memory_cap_limit(api, oracle_mod):

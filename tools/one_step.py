@@ -11,7 +11,7 @@ dr = api.DeviceBlock(hr); dg = api.DeviceBlock(hg)
 L = api.load()
 for it in range(int(os.environ.get("STEPS", "2"))):
     n0 = L.damgpu_launch_count()
-    ir = api.Index(dr); m = api.Mapper(dr, ir)
+    ir = api.Index(dr, deferred=os.environ.get("FULL_SORT") is None); m = api.Mapper(dr, ir)
     ig = api.Index(dg); m.match(dg, ig, 0, 1); ig.free()
     dg.complement(); ig = api.Index(dg); m.match(dg, ig, 1, 0); ig.free(); dg.complement()
     rep = m.report(dg, 0.85, 100, (.25, .25, .25, .25), 1)
