@@ -331,7 +331,7 @@ class Report:
         v = (C.c_int64 * 8)()
         load().damgpu_report_stats(self.h, v)
         return dict(nalign=v[0], nwaves=v[1], ncells=v[2], h2=v[3], overflow_jobs=v[4],
-                    empty_band=v[5], align_ms=v[6] / 1000.0)
+                    empty_band=v[5], align_ms=v[6] / 1000.0, trace_fails=v[7])
 
     def write_las(self, fam, directory, aname, bname, nfiles, tspace):
         rc = load().damgpu_report_write_las(self.h, fam, directory.encode(), aname.encode(),

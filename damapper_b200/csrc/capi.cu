@@ -442,6 +442,8 @@ damgpu_report *damgpu_mapper_report(damgpu_mapper *mm, const damgpu_dblock *whol
           g_par.spacing);
   ReportOut *r = reporter(h->m, reinterpret_cast<const DeviceBlock *>(wholeref), spec->ave_corr,
                           spec->freq, (mflag & 1) != 0, (mflag & 2) != 0, 0);
+  if (r->trace_fails != 0)                               // what LAcheck would reject (align.c:3194)
+    fatal("Reporter: %lld records fail Check_Trace_Points", (long long) r->trace_fails);
   return reinterpret_cast<damgpu_report *>(r);
 }
 
@@ -466,7 +468,7 @@ void damgpu_report_copy(const damgpu_report *rr, int family, uint8_t *out)
 void damgpu_report_stats(const damgpu_report *rr, int64_t out[8])
 { const ReportOut *r = reinterpret_cast<const ReportOut *>(rr);
   out[0] = r->nalign; out[1] = r->nwaves; out[2] = r->ncells; out[3] = r->h2_events;
-  out[4] = r->overflow_jobs; out[5] = r->empty_band; out[6] = (int64_t) (r->ms_align * 1000.f); out[7] = 0;
+  out[4] = r->overflow_jobs; out[5] = r->empty_band; out[6] = (int64_t) (r->ms_align * 1000.f); out[7] = r->trace_fails;
 }
 
 // per-"thread" files: reads [ (i*n)>>shift, ((i+1)*n)>>shift ), map.c:3148,3250-3261,2421-2428

@@ -17,6 +17,7 @@ struct DeviceBlock
   int64_t *mask_off = nullptr;  // -m: merged mask track (nreads+1 offsets into mask_pts), or null
   int32_t *mask_pts = nullptr;  //     interval end points, pairs [begin, end)
   int64_t  nmask = 0;           //     number of points
+  mutable int32_t *tile_tab = nullptr;   // first / last read of every 4096-position tile (kmer_filter.cu)
   int      nreads = 0, tfirst = 0, maxlen = 0;
   int64_t  totlen = 0, total = 0, sizeof_db = 0;
   std::vector<int64_t> h_boff;

@@ -83,32 +83,58 @@ __device__ __forceinline__ uint64_t fx_ld(const uint64_t *p)
 __device__ __forceinline__ void fx_st(uint64_t *p, uint64_t v)
 { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
 
+// per tile of FX_TILE base positions: r0 = read holding the tile's first position (largest r with
+// boff[r] <= t0) and l2 = last read starting before the tile's end; built once per block
+__global__ void __launch_bounds__(256)
+k_tile_reads(const int64_t *__restrict__ boff, int nreads, int64_t ntiles, int32_t *__restrict__ tab)
+{ const int64_t tile = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (tile >= ntiles) return;
+  const int64_t t0 = tile * FX_TILE;
+  int lo = 0, hi = nreads - 1;
+  while (lo < hi)
+    { int mid = (lo + hi + 1) >> 1;
+      if (boff[mid] <= t0) lo = mid; else hi = mid - 1;
+    }
+  int l2 = lo, h2 = nreads;
+  while (l2 < h2)
+    { int mid = (l2 + h2 + 1) >> 1;
+      if (boff[mid] < t0 + FX_TILE) l2 = mid; else h2 = mid - 1;
+    }
+  tab[2 * tile] = lo;
+  tab[2 * tile + 1] = l2;
+}
+
+// code of the k-mer whose last base sits at offset `off` of the tile (window index off+32)
+__device__ __forceinline__ uint64_t window_code(const uint64_t *s_pack, int off, uint64_t kmask)
+{ const int e = off + 32 + 1;                         // one past the last base, in bases
+  const int wj = (e - 1) >> 5;                        // word holding the last base
+  const int sh = 2 * (32 - (e - (wj << 5)));          // free low bits in that word
+  const uint64_t hiw = (wj > 0) ? s_pack[wj - 1] : 0ull, low = s_pack[wj];
+  const uint64_t c = (sh == 0) ? low : ((low >> sh) | (hiw << (64 - sh)));
+  return c & kmask;
+}
+
 // tuple_thread (map.c:466-579) with a membership test: position q of the block image is the last
 // base of a k-mer of read r iff rpos >= K-1 and q is not the terminator; the k-mer survives iff its
 // hash bit is set.  Survivors are written in extraction order: tiles are handed out by a ticket,
 // ranks inside a tile come from ballots (item-major, then warp, then lane = ascending q), the tile's
-// base from a chained scan over the tile totals.  counters: [0] ticket, [1] survivors, [2] overflow.
-__global__ void __launch_bounds__(FX_THREADS)
+// base from a chained scan over the tile totals (look-back by a whole warp, 32 predecessors per
+// round trip).  counters: [0] ticket, [1] survivors, [2] overflow.
+__global__ void __launch_bounds__(FX_THREADS, 3)
 k_extract_filtered(const uint8_t *__restrict__ bases, const int64_t *__restrict__ boff, int nreads,
-                   int64_t total, int K, int npass, const uint32_t *__restrict__ bitmap, int hshift,
-                   KmerPos *__restrict__ out, uint32_t cap, uint32_t *hist, uint64_t *tile_state,
-                   uint32_t *counters
-                   )
+                   int64_t total, int K, const int32_t *__restrict__ tile_tab,
+                   const uint32_t *__restrict__ bitmap, int hshift, KmerPos *__restrict__ out,
+                   uint32_t cap, uint64_t *tile_state, uint32_t *counters)
 { __shared__ uint64_t s_pack[FX_TILE / 32 + 2];
   __shared__ int64_t  s_boff[FX_MAXSPAN + 2];
-  __shared__ uint32_t s_hist[8 * 256];
   __shared__ uint32_t s_cnt[FX_ITEMS * FX_WARPS];
   __shared__ uint32_t s_wtot[4];
-  __shared__ int      s_r0, s_nspan;
   __shared__ uint32_t s_tile;
   __shared__ uint64_t s_excl;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t kmask = (K == 32) ? ~0ull : ((1ull << (2 * K)) - 1);
   const uint32_t lt = (1u << lane) - 1;
-
-  for (int i = tid; i < npass * 256; i += FX_THREADS)
-    s_hist[i] = 0;
 
   const int64_t ntiles = (total + FX_TILE - 1) / FX_TILE;
   while (true)
@@ -120,6 +146,9 @@ k_extract_filtered(const uint8_t *__restrict__ bases, const int64_t *__restrict_
       if (tile >= ntiles)
         break;
       const int64_t t0 = tile * FX_TILE;
+      const int r0 = __ldg(&tile_tab[2 * tile]);
+      const int nspan = __ldg(&tile_tab[2 * tile + 1]) - r0 + 1;    // entries r0 .. l2, plus boff[l2+1]
+      const bool cached = (nspan <= FX_MAXSPAN);
 
       for (int c = tid; c < (FX_TILE + 32) / 16; c += FX_THREADS)
         { int64_t q = t0 - 32 + (int64_t) c * 16;
@@ -128,8 +157,7 @@ k_extract_filtered(const uint8_t *__restrict__ bases, const int64_t *__restrict_
           // without it faulted on B200 ("misaligned address" at this load) although every address
           // checked on the device was aligned
           if (q >= 0 && q + 16 <= total && (((uintptr_t) (bases + q)) & 15) == 0)
-            {
-              uint4 v = __ldcs(reinterpret_cast<const uint4 *>(bases + q));
+            { uint4 v = __ldcs(reinterpret_cast<const uint4 *>(bases + q));
               uint32_t x[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
               for (int j = 0; j < 4; j++)
@@ -147,82 +175,58 @@ k_extract_filtered(const uint8_t *__restrict__ bases, const int64_t *__restrict_
             }
           reinterpret_cast<uint32_t *>(s_pack)[c ^ 1] = w;
         }
-      if (tid == 0)
-        { int lo = 0, hi = nreads - 1;
-          while (lo < hi)
-            { int mid = (lo + hi + 1) >> 1;
-              if (boff[mid] <= t0) lo = mid; else hi = mid - 1;
-            }
-          s_r0 = lo;
-          int l2 = lo, h2 = nreads;
-          while (l2 < h2)
-            { int mid = (l2 + h2 + 1) >> 1;
-              if (boff[mid] < t0 + FX_TILE) l2 = mid; else h2 = mid - 1;
-            }
-          s_nspan = l2 - lo + 1;
-        }
-      __syncthreads();
-      const int r0 = s_r0;
-      const int nspan = s_nspan;
-      const bool cached = (nspan <= FX_MAXSPAN);
       if (cached)
         for (int i = tid; i <= nspan; i += FX_THREADS)
           s_boff[i] = boff[r0 + i];
       __syncthreads();
 
-      // codes of the thread's 16 positions (0 bit in `valid` = no k-mer ends there)
-      uint64_t code[FX_ITEMS];
-      uint32_t valid = 0;
-#pragma unroll
-      for (int it = 0; it < FX_ITEMS; it++)
-        { const int off = tid + it * FX_THREADS;
-          const int64_t q = t0 + off;
-          code[it] = 0;
-          if (q >= total)
-            continue;
-          int64_t b0, b1;
-          if (cached)
-            { int lo = 0, hi = nspan - 1;
-              while (lo < hi)
-                { int mid = (lo + hi + 1) >> 1;
-                  if (s_boff[mid] <= q) lo = mid; else hi = mid - 1;
-                }
-              b0 = s_boff[lo]; b1 = s_boff[lo + 1];
-            }
-          else
-            { int lo = r0, hi = nreads - 1;
-              while (lo < hi)
-                { int mid = (lo + hi + 1) >> 1;
-                  if (boff[mid] <= q) lo = mid; else hi = mid - 1;
-                }
-              b0 = boff[lo]; b1 = boff[lo + 1];
-            }
-          if (q - b0 < K - 1 || q >= b1 - 1)
-            continue;
-          const int e = off + 32 + 1;
-          const int wj = (e - 1) >> 5;
-          const int sh = 2 * (32 - (e - (wj << 5)));
-          uint64_t hiw = (wj > 0) ? s_pack[wj - 1] : 0ull, low = s_pack[wj];
-          uint64_t c = (sh == 0) ? low : ((low >> sh) | (hiw << (64 - sh)));
-          code[it] = c & kmask;
-          valid |= 1u << it;
-        }
-      // membership: all bitmap words requested before the first one is used
-      uint32_t word[FX_ITEMS];
-#pragma unroll
-      for (int it = 0; it < FX_ITEMS; it++)
-        { const uint32_t h = bit_of(code[it], hshift);
-          word[it] = ((valid >> it) & 1) ? __ldg(&bitmap[h >> 5]) : 0u;
-        }
+      // membership of the thread's 16 positions, eight lookups in flight at a time
       uint32_t keep = 0;
 #pragma unroll
-      for (int it = 0; it < FX_ITEMS; it++)
-        { const uint32_t h = bit_of(code[it], hshift);
-          const uint32_t k = (word[it] >> (h & 31)) & 1u;
-          keep |= k << it;
-          const uint32_t b = __ballot_sync(0xffffffffu, k);
-          if (lane == 0)
-            s_cnt[it * FX_WARPS + warp] = __popc(b);
+      for (int half = 0; half < 2; half++)
+        { uint32_t hsh[FX_ITEMS / 2], word[FX_ITEMS / 2];
+          uint32_t valid = 0;
+#pragma unroll
+          for (int j = 0; j < FX_ITEMS / 2; j++)
+            { const int off = tid + (half * (FX_ITEMS / 2) + j) * FX_THREADS;
+              const int64_t q = t0 + off;
+              hsh[j] = 0;
+              if (q >= total)
+                continue;
+              int64_t b0, b1;
+              if (cached)
+                { int lo = 0, hi = nspan - 1;
+                  while (lo < hi)
+                    { int mid = (lo + hi + 1) >> 1;
+                      if (s_boff[mid] <= q) lo = mid; else hi = mid - 1;
+                    }
+                  b0 = s_boff[lo]; b1 = s_boff[lo + 1];
+                }
+              else
+                { int lo = r0, hi = nreads - 1;
+                  while (lo < hi)
+                    { int mid = (lo + hi + 1) >> 1;
+                      if (boff[mid] <= q) lo = mid; else hi = mid - 1;
+                    }
+                  b0 = boff[lo]; b1 = boff[lo + 1];
+                }
+              if (q - b0 < K - 1 || q >= b1 - 1)
+                continue;
+              hsh[j] = bit_of(window_code(s_pack, off, kmask), hshift);
+              valid |= 1u << j;
+            }
+#pragma unroll
+          for (int j = 0; j < FX_ITEMS / 2; j++)
+            word[j] = ((valid >> j) & 1) ? __ldg(&bitmap[hsh[j] >> 5]) : 0u;
+#pragma unroll
+          for (int j = 0; j < FX_ITEMS / 2; j++)
+            { const int it = half * (FX_ITEMS / 2) + j;
+              const uint32_t k = (word[j] >> (hsh[j] & 31)) & 1u;
+              keep |= k << it;
+              const uint32_t b = __ballot_sync(0xffffffffu, k);
+              if (lane == 0)
+                s_cnt[it * FX_WARPS + warp] = __popc(b);
+            }
         }
       __syncthreads();
       // exclusive scan of the 128 (item, warp) counts
@@ -246,26 +250,40 @@ k_extract_filtered(const uint8_t *__restrict__ bases, const int64_t *__restrict_
         if (tid < FX_ITEMS * FX_WARPS)
           s_cnt[tid] += add;
       }
-      if (tid == 0)
+      if (warp == 0)                                    // chained scan over the tiles
         { uint64_t *st = tile_state + tile;
+          if (lane == 0)
+            fx_st(st, (tile == 0 ? FX_INC : FX_AGG) | tot);
           uint64_t excl = 0;
-          fx_st(st, (tile == 0 ? FX_INC : FX_AGG) | tot);
           if (tile > 0)
-            { const uint64_t *p = st - 1;
+            { int64_t j = tile - 1;                     // nearest predecessor not yet summed
               while (true)
-                { uint64_t v = fx_ld(p);
-                  if (v & FX_INC) { excl += v & FX_VAL; break; }
-                  if (v & FX_AGG) { excl += v & FX_VAL; p -= 1;
-                                    continue; }
-                  __nanosleep(20);
+                { const int64_t idx = j - lane;
+                  const uint64_t v = (idx >= 0) ? fx_ld(tile_state + idx) : FX_INC;
+                  const uint32_t notready = __ballot_sync(0xffffffffu, (v >> 62) == 0);
+                  const uint32_t inc = __ballot_sync(0xffffffffu, (v & FX_INC) != 0);
+                  const int first = inc ? (__ffs(inc) - 1) : 32;
+                  const uint32_t upto = (first >= 31) ? 0xffffffffu : ((2u << first) - 1);
+                  if (notready & upto)
+                    { __nanosleep(40);
+                      continue;
+                    }
+                  const uint32_t mine = ((upto >> lane) & 1u) ? (uint32_t) (v & FX_VAL) : 0u;
+                  excl += __reduce_add_sync(0xffffffffu, mine);
+                  if (first < 32)
+                    break;
+                  j -= 32;
                 }
-              fx_st(st, FX_INC | (excl + tot));
+              if (lane == 0)
+                fx_st(st, FX_INC | (excl + tot));
             }
-          s_excl = excl;
-          if (tile == ntiles - 1)
-            counters[1] = (uint32_t) (excl + tot);
-          if (excl + tot > cap)
-            counters[2] = 1;
+          if (lane == 0)
+            { s_excl = excl;
+              if (tile == ntiles - 1)
+                counters[1] = (uint32_t) (excl + tot);
+              if (excl + tot > cap)
+                counters[2] = 1;
+            }
         }
       __syncthreads();
       const uint64_t base = s_excl;
@@ -280,7 +298,8 @@ k_extract_filtered(const uint8_t *__restrict__ bases, const int64_t *__restrict_
           const uint64_t pos = base + s_cnt[it * FX_WARPS + warp] + __popc(b & lt);
           if (pos >= cap)
             continue;
-          const int64_t q = t0 + tid + it * FX_THREADS;
+          const int off = tid + it * FX_THREADS;
+          const int64_t q = t0 + off;
           int r; int64_t b0;
           if (cached)
             { int lo = 0, hi = nspan - 1;
@@ -299,16 +318,10 @@ k_extract_filtered(const uint8_t *__restrict__ bases, const int64_t *__restrict_
               r = lo; b0 = boff[lo];
             }
           KmerPos kp;
-          kp.code = code[it]; kp.rpos = (int) (q - b0); kp.read = r;
+          kp.code = window_code(s_pack, off, kmask); kp.rpos = (int) (q - b0); kp.read = r;
           __stcs(reinterpret_cast<uint4 *>(out + pos), *reinterpret_cast<uint4 *>(&kp));
-          for (int p = 0; p < npass; p++)
-            atomicAdd(&s_hist[p * 256 + ((code[it] >> (8 * p)) & 0xff)], 1u);
         }
     }
-  __syncthreads();
-  for (int i = tid; i < npass * 256; i += FX_THREADS)
-    if (s_hist[i])
-      atomicAdd(&hist[i], s_hist[i]);
 }
 
 __global__ void k_filter_sentinels(KmerPos *list, int64_t n)   // map.c:772-773
@@ -361,10 +374,15 @@ static KmerIndex *build_filtered(const KmerIndex *a, const KmerIndex *b, uint32_
     bytes[npass++] = i >> 3;
 
   const int64_t ntiles = (blk->total + FX_TILE - 1) / FX_TILE;
+  if (blk->tile_tab == nullptr)                          // reads of every tile, once per block
+    { blk->tile_tab = dalloc<int32_t>((size_t) 2 * ntiles);
+      LAUNCH(k_tile_reads, (unsigned) ((ntiles + 255) / 256), 256, 0, stream, blk->boff, blk->nreads,
+             ntiles, blk->tile_tab);
+    }
   uint32_t *hist = dalloc<uint32_t>(256 * 16);
   uint64_t *state = dalloc<uint64_t>((size_t) ntiles + 2);
   uint32_t *counters = reinterpret_cast<uint32_t *>(state + ntiles);      // 3 words used
-  int grid = sm_count() * 6;
+  int grid = sm_count() * 4;                           // resident CTAs (64 registers), tiles by ticket
   if (grid > ntiles) grid = (int) ntiles;
 
   cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
@@ -380,11 +398,9 @@ static KmerIndex *build_filtered(const KmerIndex *a, const KmerIndex *b, uint32_
   uint32_t res[3] = { 0, 0, 0 };
   while (true)
     { lst = dalloc<KmerPos>((size_t) cap + 2);
-      CUDA_CHECK(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * 256 * 16, stream));
       CUDA_CHECK(cudaMemsetAsync(state, 0, sizeof(uint64_t) * ((size_t) ntiles + 2), stream));
       LAUNCH(k_extract_filtered, grid, FX_THREADS, 0, stream, blk->bases, blk->boff, blk->nreads,
-             blk->total, K, npass, bitmap, hshift, lst, cap, hist, state, counters
-             );
+             blk->total, K, blk->tile_tab, bitmap, hshift, lst, cap, state, counters);
       CUDA_CHECK(cudaMemcpyAsync(res, counters, sizeof(res), cudaMemcpyDeviceToHost, stream));
       CUDA_CHECK(cudaStreamSynchronize(stream));
       if (res[2] == 0)
@@ -400,6 +416,7 @@ static KmerIndex *build_filtered(const KmerIndex *a, const KmerIndex *b, uint32_
   f->npass = npass;
   if (kept > 0)
     { KmerPos *tmp = dalloc<KmerPos>((size_t) kept + 2);
+      radix_histogram(lst, kept, bytes, npass, hist, stream);     // one read of the survivors
       KmerPos *rez = (KmerPos *) radix_sort16(lst, tmp, kept, bytes, npass, hist, stream);
       LAUNCH(k_filter_sentinels, 1, 1, 0, stream, rez, (int64_t) kept);
       dfree(rez == lst ? tmp : lst);

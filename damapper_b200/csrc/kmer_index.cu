@@ -446,7 +446,7 @@ void complement_block(DeviceBlock *blk, cudaStream_t stream)
 void free_block(DeviceBlock *blk)
 { if (blk == nullptr) return;
   dfree(blk->raw); dfree(blk->boff); dfree(blk->rlen);
-  dfree(blk->mask_off); dfree(blk->mask_pts);
+  dfree(blk->mask_off); dfree(blk->mask_pts); dfree(blk->tile_tab);
   delete blk;
 }
 

@@ -650,6 +650,39 @@ k_compact_out(const uint8_t *__restrict__ src, const int64_t *__restrict__ src_o
     }
 }
 
+// Check_Trace_Points (align.c:3194-3236) on every record of the dense stream, one thread per read:
+// the number of trace points must match the A interval and the B advances must add up to the B
+// interval.  Counts the records that fail (the LAcheck pass of
+// HPC.damapper, at full speed on the device).
+__global__ void __launch_bounds__(256)
+k_check_trace(const uint8_t *__restrict__ dense, const int64_t *__restrict__ off,
+              const int *__restrict__ nrec, int n, int tspace, int tbytes, unsigned long long *fails)
+{ const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const uint8_t *p = dense + off[r];
+  int bad = 0;
+  for (int k = nrec[r]; k > 0; k--)
+    { int h[6];                                         // tlen, diffs, abpos, bbpos, aepos, bepos
+      for (int j = 0; j < 6; j++)
+        h[j] = (int) ((uint32_t) p[4 * j] | ((uint32_t) p[4 * j + 1] << 8) |
+                      ((uint32_t) p[4 * j + 2] << 16) | ((uint32_t) p[4 * j + 3] << 24));
+      const int tlen = h[0];
+      const uint8_t *t = p + 40;
+      if (((h[4] - 1) / tspace - h[2] / tspace) * 2 != tlen - 2)
+        bad++;
+      else
+        { int b = h[3];
+          for (int i = 1; i < tlen; i += 2)
+            b += (tbytes == 1) ? (int) t[i] : (int) ((uint32_t) t[2 * i] | ((uint32_t) t[2 * i + 1] << 8));
+          if (b != h[5])
+            bad++;
+        }
+      p = t + (int64_t) tlen * tbytes;
+    }
+  if (bad)
+    atomicAdd(fails, (unsigned long long) bad);
+}
+
 template <typename T> static std::vector<T> d2h(const T *d, size_t n)
 { std::vector<T> v(n);
   if (n) CUDA_CHECK(cudaMemcpy(v.data(), d, sizeof(T) * n, cudaMemcpyDeviceToHost));
@@ -914,6 +947,9 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
         dstv.resize((size_t) tot);
         if (tot > 0)
           CUDA_CHECK(cudaMemcpyAsync(dstv.data(), dense, (size_t) tot, cudaMemcpyDeviceToHost, stream));
+        if (n > 0 && tot > 0)
+          LAUNCH(k_check_trace, (n + 255) / 256, 256, 0, stream, dense, d_off, fam ? R.nrec_b : R.nrec_a, n,
+                 S, (S <= 125) ? 1 : 2, d_ull + 7);       // TRACE_XOVR, align.h:45
         nrec = d2h(fam ? R.nrec_b : R.nrec_a, (size_t) n);
         int64_t total = 0;
         for (int i = 0; i < n; i++) total += nrec[i];
@@ -925,6 +961,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
     if (g_par.profile)
       out->prof = d2h(R.prof, (size_t) m->h_coff[n]);
     out->h2_events = (int64_t) d2h(d_ull + 6, 1)[0];
+    out->trace_fails = (int64_t) d2h(d_ull + 7, 1)[0];
   }
 
   TRACE("report: copy out");

@@ -13,6 +13,7 @@ struct ReportOut
   int64_t nrec_a = 0, nrec_b = 0;
   std::vector<uint8_t> prof;               // -p track bytes, (rlen-1)/S+2 per read
   int64_t nalign = 0, nwaves = 0, ncells = 0, empty_band = 0, h2_events = 0;
+  int64_t trace_fails = 0;                 // records failing Check_Trace_Points (align.c:3194), checked on the device
   int     overflow_jobs = 0;               // alignment jobs re-run by the overflow kernel
   float   ms_align = 0.f;
 };

@@ -195,7 +195,9 @@ int64_t        damgpu_report_bytes(const damgpu_report *r, int family /*0=M,1=R,
 int64_t        damgpu_report_records(const damgpu_report *r, int family);
 void           damgpu_report_copy(const damgpu_report *r, int family, uint8_t *out);
 /* nalign, nwaves, ncells (furthest-reaching cell updates, align.c:887-893), H2 events,
- * overflow-kernel jobs, empty-band events, alignment-kernel ms (when timing is on, as int us) */
+ * overflow-kernel jobs, empty-band events, alignment-kernel ms (when timing is on, as int us),
+ * records of both families that fail Check_Trace_Points (align.c:3194-3236; every record is checked
+ * on the device before it is copied back -- the LAcheck step of HPC.damapper.c:453-498; must be 0) */
 void           damgpu_report_stats(const damgpu_report *r, int64_t out[8]);
 /* write <dir>/<aname>.<bname>.M<i>.las (family 0) or <dir>/<bname>.<aname>.R<i>.las (family 1),
  * i = 1..nfiles, reads split as (i*nreads)>>log2(nfiles) (map.c:3148,3250-3261); returns 0 */

@@ -36,6 +36,7 @@ def _gpu_vs_oracle(api, orc, cfg, scale, seed, reads_filter="auto", **kw):
     assert g["prof"] == o["prof"], "-p track differs"
     for key in ("nalign", "nwaves", "ncells"):
         assert g["stats"][key] == o["stats"][key], key
+    assert g["stats"]["trace_fails"] == 0             # Check_Trace_Points of every record, on the device
     return g
 
 
