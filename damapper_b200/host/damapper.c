@@ -106,6 +106,10 @@ static double arg_real(const char *arg)
      }                                                                  \
  }
 
+/* las_post.c: built-in LAsort + LAcat / LAmerge, used when the DALIGNER programs are not installed */
+int las_sort_cat(const char *prefix, int nfiles, const char *out, int map_order, int verbose);
+int on_path(const char *prog);
+
 /* reference block k, resident between reads blocks */
 typedef struct
   { damgpu_dblock *blk;                 /* the block (complemented: only its sizes are used again) */
@@ -169,6 +173,7 @@ int main(int argc, char *argv[])
   damgpu_options opts;
   damgpu_align_spec spec;
   Ref_Cache *rcache;
+  int    builtin_sort = 0;
   damgpu_dblock *whole = NULL;                            /* whole reference, kept for the Reporter */
   uint64_t cache_budget = 0, cache_used = 0;
   Prefetch pre;
@@ -344,6 +349,10 @@ int main(int argc, char *argv[])
     if (rcache != NULL && argc > 3 && pct > 0. && damgpu_device_memory(&fr,&tot) == 0)
       cache_budget = (uint64_t) (tot * (pct < 90. ? pct : 90.) / 100.);
   }
+  /* the DALIGNER post-processing programs, or the built-in stand-in when they are not installed */
+  builtin_sort = (getenv("DAMGPU_BUILTIN_SORT") != NULL || !on_path("LAsort"));
+  if (builtin_sort && VERBOSE)
+    printf("\n  LAsort is not on PATH (or DAMGPU_BUILTIN_SORT is set): built-in sort and merge of the .las files\n");
   memset(&pre,0,sizeof(pre));
   if (argc > 2)
     prefetch_start(&pre,argv[2],MASK,MTOP,Prog_Name);
@@ -491,6 +500,25 @@ int main(int argc, char *argv[])
       dazz_close(&bblock);
       tick("release block");
 
+      if (builtin_sort)                                  /* no DALIGNER programs: las_post.c */
+        { int nfiles = 1;
+          while (2*nfiles <= NTHREADS) nfiles *= 2;
+          if ((mflag & 1) != 0)
+            { sprintf(command,"%s/%s.%s.M",SORT_PATH,broot,aroot);
+              sprintf(command+strlen(command)+1,"%s.%s.las",broot,aroot);
+              if (las_sort_cat(command,nfiles,command+strlen(command)+1,MAP_ORDER,VERBOSE))
+                Clean_Exit(1);
+            }
+          if ((mflag & 2) != 0)
+            { sprintf(command,"%s/%s.%s.R",SORT_PATH,aroot,broot);
+              sprintf(command+strlen(command)+1,"%s.%s.las",aroot,broot);
+              if (las_sort_cat(command,nfiles,command+strlen(command)+1,MAP_ORDER,VERBOSE))
+                Clean_Exit(1);
+            }
+          tick("built-in LAsort / LAcat / LAmerge");
+          free(broot);
+          continue;
+        }
       if ((mflag & 1) != 0)                              /* damapper.c:893-901 */
         { sprintf(command,"LAsort %s %s %s/%s.%s.M%c.las",VERBOSE?"-v":"",MAP_ORDER?"-a":"",
                           SORT_PATH,broot,aroot,'@');

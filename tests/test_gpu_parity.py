@@ -505,6 +505,35 @@ def test_host_driver_cli(api, tmp_path):
     assert las.canonical_stream(m) == g["a"].tobytes()
     assert las.canonical_stream(r) == g["b"].tobytes()
     assert open(os.path.join(wd, ".reads.prof.data"), "rb").read() == g["prof"].tobytes()
+    # the same run without the DALIGNER programs: the driver sorts and merges the per-thread files
+    # itself (las_post.c) and leaves the final reads.ref.las / ref.reads.las
+    env2 = dict(env)
+    env2["DAMGPU_BUILTIN_SORT"] = "1"
+    os.remove(os.path.join(wd, ".reads.prof.data"))
+    p = subprocess.run([exe, "-v", "-T4", "-P" + os.path.join(wd, "tmp")] + list(flags) + ["ref.dam", "reads.db"],
+                       cwd=wd, env=env2, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr
+    assert "built-in sort" in p.stdout
+    for fname, stream in (("reads.ref.las", g["a"].tobytes()), ("ref.reads.las", g["b"].tobytes())):
+        ts, recs = las.read_las(os.path.join(wd, fname))
+        want = las.stream_records(stream, ts)
+        assert len(recs) == len(want) > 0
+
+        def chains(rs):
+            out = []
+            for r in rs:
+                key = (r["tlen"], r["diffs"], r["abpos"], r["bbpos"], r["aepos"], r["bepos"], r["flags"],
+                       r["aread"], r["bread"], r["trace"].tobytes())
+                if r["flags"] & 0x8 and out:          # NEXT: continues the chain
+                    out[-1].append(key)
+                else:
+                    out.append([key])
+            return out
+        got_c, want_c = chains(recs), chains(want)
+        assert sorted(map(tuple, got_c)) == sorted(map(tuple, want_c))     # same chains, whole
+        heads = [(c[0][7], c[0][2]) for c in got_c]                         # (aread, abpos), -a order
+        assert heads == sorted(heads)
+        assert las.check_trace_points(recs, ts) == 0
     # error behaviour of the reference CLI is kept
     p = subprocess.run([exe, "-N", "ref.dam", "reads.db"], cwd=wd, env=env, capture_output=True, text=True)
     assert p.returncode == 1 and "Cannot specify N flag without C also" in p.stderr
