@@ -154,6 +154,11 @@ int damgpu_init(int device)
   g_chain_async = (getenv("DAMGPU_SYNC_CHAIN") == nullptr);
   if (const char *t = getenv("DAMGPU_SLOTS"))
     g_align_slots = atoi(t);
+  if (const char *t = getenv("DAMGPU_RADIX"))
+    g_radix_reload = !strcmp(t, "reload");
+  g_radix_pf = g_sms;                                    // one tile per SM ahead (flat between 64 and 200 on B200)
+  if (const char *t = getenv("DAMGPU_RADIX_PF"))
+    g_radix_pf = atoi(t);
   if (const char *t = getenv("DAMGPU_FILTER"))
     g_filter_mode = !strcmp(t, "off") ? 0 : !strcmp(t, "always") ? 2 : 1;
   if (const char *t = getenv("DAMGPU_FILTER_BITS"))

@@ -79,5 +79,7 @@ void radix_histogram(const void *recs, uint32_t n, const int *bytes, int npass, 
                      cudaStream_t stream);
 // event-timed duration of the radix passes of the last radix_sort16 call when timing is on
 extern bool   g_time_kernels;
+extern int    g_radix_pf;
+extern bool   g_radix_reload;      // radix pass variant (radix_sort.cu)
 
 }  // namespace damgpu

@@ -117,10 +117,14 @@ __global__ void __launch_bounds__(256) k_radix_prefix(uint32_t *hist)
 
 // W32 = 32-bit word of the record holding the key byte (compile time), psel = PRMT selector that
 // moves that byte to bits 0..7: the digit costs one instruction wherever it is needed.
-template <int W32>
-__global__ void __launch_bounds__(RS_THREADS, 2)
+// RELOAD: only the key word of every record is loaded before the ranking (the 64-byte sectors come
+// from DRAM either way and stay in L2); the whole records are read a second time, from L2, when they
+// are staged.  No record lives in registers across the ranking, so three CTAs fit an SM instead of two.
+template <int W32, bool RELOAD>
+__global__ void __launch_bounds__(RS_THREADS, RELOAD ? 3 : 2)
 k_radix_pass(const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t n, uint32_t psel,
-             const uint32_t *__restrict__ gbase, uint32_t *tile_state, uint32_t *tile_counter)
+             const uint32_t *__restrict__ gbase, uint32_t *tile_state, uint32_t *tile_counter,
+             uint32_t pf_dist)
 {
 #define REC_DIGIT(r) __byte_perm((W32 == 0) ? (r).x : (W32 == 1) ? (r).y : (W32 == 2) ? (r).z : (r).w, 0, psel)
   extern __shared__ uint4 stage[];                    // 72 KB; the first 12 KB alias the counters
@@ -139,27 +143,54 @@ k_radix_pass(const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t n, 
     wh[i] = 0;
   __syncthreads();
   const uint32_t tile   = s_tile;
+  // the tile that a CTA will pick up pf_dist tickets from now is pulled into L2 by the copy engine,
+  // so DRAM keeps streaming while the resident CTAs are in their ranking phases
+  if (tid == 0 && pf_dist != 0 && (uint64_t) (tile + pf_dist + 1) * RS_TILE <= n)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+                 :: "l"(in + (size_t) (tile + pf_dist) * RS_TILE), "r"((uint32_t) RS_SMEM) : "memory");
   const uint32_t tbase  = tile * (uint32_t) RS_TILE;
   const uint32_t nvalid = (n - tbase < (uint32_t) RS_TILE) ? n - tbase : (uint32_t) RS_TILE;
   const uint4 *src = in + tbase + warp * (32 * RS_ITEMS) + lane;
 
-  uint4 rec[RS_ITEMS];
-  if (nvalid == (uint32_t) RS_TILE)                   // every tile but the last: no bounds tests
-    {
+  uint4 rec[RELOAD ? 1 : RS_ITEMS];
+  uint32_t dg[RS_ITEMS];
+  const uint32_t rbase = tbase + warp * (32 * RS_ITEMS) + lane;         // index of this thread's item 0
+  if (RELOAD)
+    { const uint32_t *kw = reinterpret_cast<const uint32_t *>(src) + W32;
+      if (nvalid == (uint32_t) RS_TILE)
+        {
 #pragma unroll
-      for (int i = 0; i < RS_ITEMS; i++)
-        rec[i] = __ldcs(src + i * 32);
+          for (int i = 0; i < RS_ITEMS; i++)
+            dg[i] = __byte_perm(__ldg(kw + i * 128), 0, psel);
+        }
+      else
+        {
+#pragma unroll
+          for (int i = 0; i < RS_ITEMS; i++)
+            dg[i] = (rbase + i * 32 < n) ? __byte_perm(__ldg(kw + i * 128), 0, psel) : 255u;
+        }
     }
-  else                                                // padding = all ones: digit 255, ranks after
-    { const uint32_t base = tbase + warp * (32 * RS_ITEMS) + lane;      // every real 255 of the tile
+  else
+    { if (nvalid == (uint32_t) RS_TILE)               // every tile but the last: no bounds tests
+        {
+#pragma unroll
+          for (int i = 0; i < RS_ITEMS; i++)
+            rec[RELOAD ? 0 : i] = __ldcs(src + i * 32);
+        }
+      else                                            // padding = all ones: digit 255, ranks after
+        {                                             // every real 255 of the tile
+#pragma unroll
+          for (int i = 0; i < RS_ITEMS; i++)
+            rec[RELOAD ? 0 : i] = (rbase + i * 32 < n) ? __ldcs(src + i * 32)
+                                         : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        }
 #pragma unroll
       for (int i = 0; i < RS_ITEMS; i++)
-        rec[i] = (base + i * 32 < n) ? __ldcs(src + i * 32)
-                                     : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        dg[i] = REC_DIGIT(rec[RELOAD ? 0 : i]);
     }
 #pragma unroll
   for (int i = 0; i < RS_ITEMS; i++)
-    atomicAdd(&wh[REC_DIGIT(rec[i])], 1u);
+    atomicAdd(&wh[dg[i]], 1u);
   __syncthreads();
 
   // digit d = tid (threads 256.. only take part in the barriers)
@@ -202,7 +233,7 @@ k_radix_pass(const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t n, 
   uint32_t pos[RS_ITEMS];
 #pragma unroll
   for (int i = 0; i < RS_ITEMS; i++)
-    { const uint32_t dig   = REC_DIGIT(rec[i]);
+    { const uint32_t dig   = dg[i];
       const uint32_t peers = match_digit(dig);
       uint32_t old = 0;
       if ((peers & lt) == 0)
@@ -210,9 +241,34 @@ k_radix_pass(const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t n, 
       pos[i] = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1) + __popc(peers & lt);
     }
   __syncthreads();                                    // counters die, staging area is live
+  if (RELOAD)
+    { if (nvalid == (uint32_t) RS_TILE)
+        { uint4 r[RS_ITEMS / 2];                      // second read of the tile, from L2; six in flight
 #pragma unroll
-  for (int i = 0; i < RS_ITEMS; i++)
-    stage[pos[i]] = rec[i];
+          for (int h = 0; h < 2; h++)
+            {
+#pragma unroll
+              for (int i = 0; i < RS_ITEMS / 2; i++)
+                r[i] = __ldcs(src + (h * (RS_ITEMS / 2) + i) * 32);
+#pragma unroll
+              for (int i = 0; i < RS_ITEMS / 2; i++)
+                stage[pos[h * (RS_ITEMS / 2) + i]] = r[i];
+            }
+        }
+      else
+        {
+#pragma unroll
+          for (int i = 0; i < RS_ITEMS; i++)
+            if (rbase + i * 32 < n)                   // padding ranks behind every real record: not staged
+              stage[pos[i]] = __ldcs(src + i * 32);
+        }
+    }
+  else
+    {
+#pragma unroll
+      for (int i = 0; i < RS_ITEMS; i++)
+        stage[pos[i]] = rec[RELOAD ? 0 : i];
+    }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged data -> async proxy
 
   uint32_t gdst = 0;
@@ -256,13 +312,15 @@ k_radix_pass(const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t n, 
 #undef REC_DIGIT
 }
 
-typedef void (*radix_pass_fn)(const uint4 *, uint4 *, uint32_t, uint32_t, const uint32_t *, uint32_t *, uint32_t *);
+bool g_radix_reload = false;                           // DAMGPU_RADIX=reload|regs
+int  g_radix_pf = 0;                                   // DAMGPU_RADIX_PF: L2 prefetch distance in tiles
+typedef void (*radix_pass_fn)(const uint4 *, uint4 *, uint32_t, uint32_t, const uint32_t *, uint32_t *, uint32_t *, uint32_t);
 static radix_pass_fn radix_pass_for(int byte)
 { switch (byte >> 2)
-    { case 0:  return k_radix_pass<0>;
-      case 1:  return k_radix_pass<1>;
-      case 2:  return k_radix_pass<2>;
-      default: return k_radix_pass<3>;
+    { case 0:  return g_radix_reload ? k_radix_pass<0, true> : k_radix_pass<0, false>;
+      case 1:  return g_radix_reload ? k_radix_pass<1, true> : k_radix_pass<1, false>;
+      case 2:  return g_radix_reload ? k_radix_pass<2, true> : k_radix_pass<2, false>;
+      default: return g_radix_reload ? k_radix_pass<3, true> : k_radix_pass<3, false>;
     }
 }
 
@@ -288,18 +346,21 @@ void *radix_sort16(void *a, void *b, uint32_t n, const int *bytes, int npass, ui
   uint32_t *state = dalloc<uint32_t>((size_t) ntiles * 256 + 1);
   uint32_t *counter = state + (size_t) ntiles * 256;
 
-  static bool attr_set = false;
-  if (!attr_set)
+  static int attr_set = -1;
+  if (attr_set != (int) g_radix_reload)
     { for (int w = 0; w < 4; w++)
-        CUDA_CHECK(cudaFuncSetAttribute(radix_pass_for(4 * w), cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM));
-      attr_set = true;
+        { CUDA_CHECK(cudaFuncSetAttribute(radix_pass_for(4 * w), cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM));
+          if (g_radix_reload)
+            CUDA_CHECK(cudaFuncSetAttribute(radix_pass_for(4 * w), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        }
+      attr_set = (int) g_radix_reload;
     }
   LAUNCH(k_radix_prefix, npass, 256, 0, stream, hist);
   uint4 *src = (uint4 *) a, *dst = (uint4 *) b;
   for (int p = 0; p < npass; p++)
     { CUDA_CHECK(cudaMemsetAsync(state, 0, sizeof(uint32_t) * ((size_t) ntiles * 256 + 1), stream));
       LAUNCH(radix_pass_for(bytes[p]), ntiles, RS_THREADS, RS_SMEM, stream, src, dst, n,
-             0x4440u | (uint32_t) (bytes[p] & 3), hist + p * 256, state, counter);
+             0x4440u | (uint32_t) (bytes[p] & 3), hist + p * 256, state, counter, (uint32_t) g_radix_pf);
       uint4 *t = src; src = dst; dst = t;
     }
   dfree(state);                                        // stream-ordered reuse (cache_alloc)
