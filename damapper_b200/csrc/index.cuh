@@ -66,6 +66,7 @@ void         free_index(KmerIndex *idx);
 KmerIndex   *sort_kmers_deferred(const DeviceBlock *blk, int K, int suppress, cudaStream_t stream);
 const KmerIndex *reads_view(const KmerIndex *a, const KmerIndex *b, cudaStream_t stream);
 void         materialize_index(KmerIndex *idx, cudaStream_t stream);
+void         ensure_tile_tab(const DeviceBlock *blk, cudaStream_t stream);   // blk->tile_tab (4096-position tiles)
 extern int   g_filter_mode, g_filter_log2;
 extern float g_filter_times[4];
 

@@ -104,6 +104,15 @@ k_tile_reads(const int64_t *__restrict__ boff, int nreads, int64_t ntiles, int32
   tab[2 * tile + 1] = l2;
 }
 
+void ensure_tile_tab(const DeviceBlock *blk, cudaStream_t stream)
+{ if (blk->tile_tab != nullptr || blk->nreads == 0)
+    return;
+  const int64_t ntiles = (blk->total + FX_TILE - 1) / FX_TILE;
+  blk->tile_tab = dalloc<int32_t>((size_t) 2 * ntiles);
+  LAUNCH(k_tile_reads, (unsigned) ((ntiles + 255) / 256), 256, 0, stream, blk->boff, blk->nreads,
+         ntiles, blk->tile_tab);
+}
+
 // code of the k-mer whose last base sits at offset `off` of the tile (window index off+32)
 __device__ __forceinline__ uint64_t window_code(const uint64_t *s_pack, int off, uint64_t kmask)
 { const int e = off + 32 + 1;                         // one past the last base, in bases
@@ -374,11 +383,7 @@ static KmerIndex *build_filtered(const KmerIndex *a, const KmerIndex *b, uint32_
     bytes[npass++] = i >> 3;
 
   const int64_t ntiles = (blk->total + FX_TILE - 1) / FX_TILE;
-  if (blk->tile_tab == nullptr)                          // reads of every tile, once per block
-    { blk->tile_tab = dalloc<int32_t>((size_t) 2 * ntiles);
-      LAUNCH(k_tile_reads, (unsigned) ((ntiles + 255) / 256), 256, 0, stream, blk->boff, blk->nreads,
-             ntiles, blk->tile_tab);
-    }
+  ensure_tile_tab(blk, stream);                          // reads of every tile, once per block
   uint32_t *hist = dalloc<uint32_t>(256 * 16);
   uint64_t *state = dalloc<uint64_t>((size_t) ntiles + 2);
   uint32_t *counters = reinterpret_cast<uint32_t *>(state + ntiles);      // 3 words used

@@ -13,7 +13,8 @@ namespace damgpu {
 
 constexpr int EX_THREADS = 256;
 constexpr int EX_ITEMS   = 16;
-constexpr int EX_TILE    = EX_THREADS * EX_ITEMS;     // base positions per tile
+constexpr int EX_TILE    = EX_THREADS * EX_ITEMS;     // base positions per tile (= the tile of blk->tile_tab)
+static_assert(EX_TILE == 4096, "tile_tab is built for 4096-position tiles");
 constexpr int EX_MAXSPAN = 512;                       // read starts cached per tile
 
 // Tile-local 2-bit packing: word j (64 bit) holds bases 32j..32j+31 of the window, first base
@@ -21,12 +22,12 @@ constexpr int EX_MAXSPAN = 512;                       // read starts cached per 
 __global__ void __launch_bounds__(EX_THREADS)
 k_extract(const uint8_t *__restrict__ bases, const int64_t *__restrict__ boff, int nreads,
           int64_t total, int K, int npass, KmerPos *__restrict__ list, uint32_t *hist,
-          const int64_t *__restrict__ mask_off, const int32_t *__restrict__ mask_pts)
+          const int64_t *__restrict__ mask_off, const int32_t *__restrict__ mask_pts,
+          const int32_t *__restrict__ tile_tab)
 { // window = [t0-32, t0+EX_TILE): 32 bases of left context (K <= 32)
   __shared__ uint64_t s_pack[EX_TILE / 32 + 2];
   __shared__ int64_t  s_boff[EX_MAXSPAN + 2];
   __shared__ uint32_t s_hist[8 * 256];
-  __shared__ int      s_r0, s_nspan;
 
   const int tid = threadIdx.x;
   const uint64_t kmask = (K == 32) ? ~0ull : ((1ull << (2 * K)) - 1);
@@ -63,26 +64,11 @@ k_extract(const uint8_t *__restrict__ bases, const int64_t *__restrict__ boff, i
           reinterpret_cast<uint32_t *>(s_pack)[c ^ 1] = w;   // big-endian pairs inside a u64
         }
 
-      // reads overlapping the tile: r0 = read containing t0 (largest r with boff[r] <= t0)
-      if (tid == 0)
-        { int lo = 0, hi = nreads - 1;
-          while (lo < hi)
-            { int mid = (lo + hi + 1) >> 1;
-              if (boff[mid] <= t0) lo = mid; else hi = mid - 1;
-            }
-          s_r0 = lo;
-          int e = lo;                                  // reads starting before the tile end
-          int l2 = lo, h2 = nreads;
-          while (l2 < h2)
-            { int mid = (l2 + h2 + 1) >> 1;
-              if (boff[mid] < t0 + EX_TILE) l2 = mid; else h2 = mid - 1;
-            }
-          e = l2;
-          s_nspan = e - lo + 1;                       // entries r0 .. e, plus boff[e+1]
-        }
+      // reads overlapping the tile, from the per-tile table (k_tile_reads): r0 = read containing t0
+      // (largest r with boff[r] <= t0), l2 = last read starting before the tile end
+      const int r0 = __ldg(&tile_tab[2 * tile]);
+      const int nspan = __ldg(&tile_tab[2 * tile + 1]) - r0 + 1;      // entries r0 .. l2, plus boff[l2+1]
       __syncthreads();
-      const int r0 = s_r0;
-      const int nspan = s_nspan;
       const bool cached = (nspan <= EX_MAXSPAN);
       if (cached)
         for (int i = tid; i <= nspan; i += EX_THREADS)
@@ -483,8 +469,9 @@ KmerIndex *sort_kmers(const DeviceBlock *blk, int K, int suppress, cudaStream_t 
     { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
       cudaEventRecord(e0, stream);
     }
+  ensure_tile_tab(blk, stream);
   LAUNCH(k_extract, grid, EX_THREADS, 0, stream, blk->bases, blk->boff, nreads, blk->total, K,
-         npass, a, hist, blk->mask_off, blk->mask_pts);
+         npass, a, hist, blk->mask_off, blk->mask_pts, blk->tile_tab);
   uint32_t nlist = n;                                  // records that go into the sort
   if (blk->mask_off != nullptr)                        // -m: squeeze out the masked slots, in order
     { uint32_t *keep = dalloc<uint32_t>(n);
