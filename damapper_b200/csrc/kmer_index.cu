@@ -298,12 +298,14 @@ DeviceBlock *upload_block_packed(const uint8_t *packed, const int64_t *poff, int
   blk->nreads = nreads; blk->tfirst = tfirst; blk->maxlen = maxlen; blk->totlen = totlen;
   blk->sizeof_db = sizeof_db;
   blk->total = boff[nreads];
+  TRACE(nullptr);
   blk->raw = dalloc<uint8_t>((size_t) blk->total + 2 * BLOCK_SLACK);
   blk->bases = blk->raw + BLOCK_SLACK;
   blk->boff = dalloc<int64_t>(nreads + 1);
   blk->rlen = dalloc<int32_t>(nreads + 1);
   uint8_t *d_packed = dalloc<uint8_t>((size_t) packed_bytes + 16);
   int64_t *d_poff = dalloc<int64_t>(nreads + 1);
+  TRACE("upload_packed: allocations");
   CUDA_CHECK(cudaMemcpyAsync(d_packed, packed, (size_t) packed_bytes, cudaMemcpyHostToDevice, stream));
   CUDA_CHECK(cudaMemcpyAsync(d_poff, poff, sizeof(int64_t) * nreads, cudaMemcpyHostToDevice, stream));
   CUDA_CHECK(cudaMemcpyAsync(blk->boff, boff, sizeof(int64_t) * (nreads + 1), cudaMemcpyHostToDevice, stream));
@@ -318,6 +320,7 @@ DeviceBlock *upload_block_packed(const uint8_t *packed, const int64_t *poff, int
   blk->h_boff.assign(boff, boff + nreads + 1);
   blk->h_rlen.assign(rlen, rlen + nreads);
   CUDA_CHECK(cudaStreamSynchronize(stream));
+  TRACE("upload_packed: copies + unpack");
   dfree(d_packed); dfree(d_poff);
   return blk;
 }

@@ -1,0 +1,22 @@
+"""Dev: whole-process phases of the host driver on the C2 workload (DAMGPU_TIMING=1)."""
+import os, sys, subprocess, tempfile, time, shutil
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from damapper_b200 import synth, dazzdb
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+exe = os.path.join(ROOT, "damapper_b200", "damapper")
+contigs, rb, rl = synth.make_config("C2", scale=float(os.environ.get("SCALE", "1.0")), seed=7)
+wd = tempfile.mkdtemp(prefix="clit_")
+dazzdb.write_db(os.path.join(wd, "ref.dam"), contigs, is_dam=True)
+dazzdb.write_db(os.path.join(wd, "reads.db"), (rb, rl))
+os.makedirs(os.path.join(wd, "tmp"))
+env = dict(os.environ); env["DAMGPU_TIMING"] = "1"; env["DAMGPU_BUILTIN_SORT"] = "1"
+if os.environ.get("TRACE"): env["DAMGPU_TRACE"] = "1"
+for it in range(3):
+    t0 = time.time()
+    p = subprocess.run([exe, "-T16", "-M32", "-P" + os.path.join(wd, "tmp"), "ref.dam", "reads.db"], cwd=wd, env=env,
+                       capture_output=True, text=True)
+    dt = time.time() - t0
+    print("run %d: rc %d wall %.3f s" % (it, p.returncode, dt))
+    if it == 2:
+        print(p.stderr[-3000:])
+shutil.rmtree(wd, ignore_errors=True)
