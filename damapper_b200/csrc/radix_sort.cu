@@ -10,8 +10,13 @@
 
 namespace damgpu {
 
-constexpr int RS_THREADS = 384;
-constexpr int RS_ITEMS   = 12;
+#ifndef RS_THREADS_V                                   // build-time variants (tools/sort_bench.py)
+#define RS_THREADS_V 384
+#define RS_ITEMS_V   12
+#define RS_MINB_V    2
+#endif
+constexpr int RS_THREADS = RS_THREADS_V;
+constexpr int RS_ITEMS   = RS_ITEMS_V;
 constexpr int RS_TILE    = RS_THREADS * RS_ITEMS;      // records per tile (4608 = 72 KB staged)
 constexpr int RS_WARPS   = RS_THREADS / 32;
 constexpr int RS_PROBE   = 8;                          // predecessors fetched per look-back round
@@ -121,7 +126,7 @@ __global__ void __launch_bounds__(256) k_radix_prefix(uint32_t *hist)
 // from DRAM either way and stay in L2); the whole records are read a second time, from L2, when they
 // are staged.  No record lives in registers across the ranking, so three CTAs fit an SM instead of two.
 template <int W32, bool RELOAD>
-__global__ void __launch_bounds__(RS_THREADS, RELOAD ? 3 : 2)
+__global__ void __launch_bounds__(RS_THREADS, RELOAD ? 3 : RS_MINB_V)
 k_radix_pass(const uint4 *__restrict__ in, uint4 *__restrict__ out, uint32_t n, uint32_t psel,
              const uint32_t *__restrict__ gbase, uint32_t *tile_state, uint32_t *tile_counter,
              uint32_t pf_dist)
