@@ -167,11 +167,51 @@ __device__ void consider(const Acc nd, int h, int ar, int br,
 // would pass 32 entries or the group 1024 nodes, the state is written out and the GENERAL path takes
 // over for the rest of the group: sorted slice in shared memory (spilling to global scratch), nodes
 // in global scratch, the lanes scan the slice 32 entries at a time.  Both give the same result.
+// Hand-out order of the reads: longest seed lists first (a read with its true location in this
+// orientation carries ~10x the seeds of one without, and the kernel ends with its longest reads).
+// first[r] = index of read r's first seed, bucket = bit length of its seed count; reads are ordered
+// by descending bucket (order inside a bucket is irrelevant: reads are independent of each other).
+__global__ void __launch_bounds__(256)
+k_read_seed_spans(const SeedPair *__restrict__ hits, int64_t nhits, int nreads, int64_t *__restrict__ first,
+                  int *__restrict__ bucket, int *bucket_count)
+{ const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nreads) return;
+  int64_t lo = 0, hi = nhits;
+  while (lo < hi)
+    { int64_t mid = (lo + hi) >> 1;
+      if (hits[mid].aread < r) lo = mid + 1; else hi = mid;
+    }
+  const int64_t b = lo;
+  hi = nhits;
+  while (lo < hi)
+    { int64_t mid = (lo + hi) >> 1;
+      if (hits[mid].aread <= r) lo = mid + 1; else hi = mid;
+    }
+  const int64_t cnt = lo - b;
+  first[r] = (cnt > 0) ? b : -1;
+  const int k = (cnt > 0) ? 64 - __clzll((unsigned long long) cnt) : 0;      // 0..40
+  bucket[r] = k;
+  atomicAdd(&bucket_count[k], 1);
+}
+
+__global__ void k_read_order(const int *__restrict__ bucket, int nreads, int *bucket_count, int *__restrict__ order)
+{ __shared__ int start[64];
+  if (threadIdx.x == 0)
+    { int run = 0;
+      for (int k = 63; k >= 0; k--)                      // descending bit length
+        { start[k] = run; run += bucket_count[k]; }
+    }
+  __syncthreads();
+  for (int r = threadIdx.x; r < nreads; r += blockDim.x)
+    order[atomicAdd(&start[bucket[r]], 1)] = r;
+}
+
 __global__ void __launch_bounds__(CH_WARPS * 32)
 k_chain(const SeedPair *__restrict__ hits, int64_t nhits, int nreads, int K, int bstart, int comp,
         int profile, int spacing, ChainScratch sc, Candidate *cand, int *cand_top, int cand_cap,
         uint32_t *jumps, unsigned long long *jump_top, unsigned long long jump_cap,
-        int *head, int16_t *cover, const int64_t *__restrict__ coff, int *overflow, int *read_counter)
+        int *head, int16_t *cover, const int64_t *__restrict__ coff, int *overflow, int *read_counter,
+        const int *__restrict__ order, const int64_t *__restrict__ first)
 { __shared__ int4   s_S[CH_WARPS][CH_SCAP];
   __shared__ NodeSm s_N[CH_WARPS][CH_NCAP];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -183,14 +223,9 @@ k_chain(const SeedPair *__restrict__ hits, int64_t nhits, int nreads, int K, int
     if (lane == 0) ar = atomicAdd(read_counter, 1);
     ar = __shfl_sync(FULL, ar, 0);
     if (ar >= nreads) break;
-
-    int64_t lo = 0, hi = nhits;                        // seed range of read ar
-    while (lo < hi)
-      { int64_t mid = (lo + hi) >> 1;
-        if (hits[mid].aread < ar) lo = mid + 1; else hi = mid;
-      }
-    int64_t nidx = lo;
-    if (nidx >= nhits || hits[nidx].aread != ar) continue;
+    ar = order[ar];                                    // ticket -> read, longest seed lists first
+    int64_t nidx = first[ar];                          // seed range of read ar
+    if (nidx < 0) break;                               // only reads without seeds are left
 
     int chead = head[ar];
 
@@ -646,15 +681,24 @@ void chain_seeds(Mapper *m, SeedSet *ss, int bstart, int comp, cudaStream_t stre
   CUDA_CHECK(cudaStreamWaitEvent(g_ca.stream, g_ca.ready, 0));
   int *read_counter = m->cand_top + 2;                  // reads are handed out by a counter
   CUDA_CHECK(cudaMemsetAsync(read_counter, 0, sizeof(int), g_ca.stream));
+  int64_t *first = dalloc<int64_t>((size_t) n + 1);      // hand-out order: longest seed lists first
+  int *order = dalloc<int>((size_t) 2 * n + 64);
+  int *bucket = order + n, *bucket_count = order + 2 * n;
+  CUDA_CHECK(cudaMemsetAsync(bucket_count, 0, sizeof(int) * 64, g_ca.stream));
+  LAUNCH(k_read_seed_spans, (n + 255) / 256, 256, 0, g_ca.stream, ss->hits, nhits, n, first, bucket, bucket_count);
+  LAUNCH(k_read_order, 1, 1024, 0, g_ca.stream, bucket, n, bucket_count, order);
   int grid = (n + CH_WARPS - 1) / CH_WARPS;
   if (grid > sm_count() * CH_CTAS) grid = sm_count() * CH_CTAS;
   LAUNCH(k_chain, grid, CH_WARPS * 32, 0, g_ca.stream, ss->hits, nhits, n, g_par.kmer,
          bstart, comp, g_par.profile, g_par.spacing, sc, m->cand, m->cand_top, m->cand_cap, m->jumps,
-         m->jump_top, (unsigned long long) m->jump_cap, m->head, m->cover, m->coff, m->overflow, read_counter);
+         m->jump_top, (unsigned long long) m->jump_cap, m->head, m->cover, m->coff, m->overflow, read_counter,
+         order, first);
   CUDA_CHECK(cudaEventRecord(g_ca.done, g_ca.stream));
   g_ca.busy = true;
   g_ca.pending.push_back(scratch);
   g_ca.pending.push_back(sc.S);
+  g_ca.pending.push_back(first);
+  g_ca.pending.push_back(order);
   if (async)                                           // the seeds now belong to the pending call
     { g_ca.pending.push_back(ss->hits);
       ss->hits = nullptr;
