@@ -753,9 +753,9 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   uint16_t      *d_tscr = dalloc<uint16_t>(tscr);
   unsigned char *d_big = nullptr;
   int           *d_ctr = dalloc<int>(8);               // job counter, aln_top, nfailed, nlist
-  unsigned long long *d_ull = dalloc<unsigned long long>(8);   // trace_top, stats[4], h2
+  unsigned long long *d_ull = dalloc<unsigned long long>(10);  // trace_top, stats[7] (1..7), trace-check failures (8)
   CUDA_CHECK(cudaMemsetAsync(d_ctr, 0, sizeof(int) * 8, stream));
-  CUDA_CHECK(cudaMemsetAsync(d_ull, 0, sizeof(unsigned long long) * 8, stream));
+  CUDA_CHECK(cudaMemsetAsync(d_ull, 0, sizeof(unsigned long long) * 10, stream));
 
   int       aln_cap = njobs * 2 + 1024;
   long long trace_cap = (long long) aln_cap * (4 * (rd->maxlen / S + 4));
@@ -949,7 +949,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
           CUDA_CHECK(cudaMemcpyAsync(dstv.data(), dense, (size_t) tot, cudaMemcpyDeviceToHost, stream));
         if (n > 0 && tot > 0)
           LAUNCH(k_check_trace, (n + 255) / 256, 256, 0, stream, dense, d_off, fam ? R.nrec_b : R.nrec_a, n,
-                 S, (S <= 125) ? 1 : 2, d_ull + 7);       // TRACE_XOVR, align.h:45
+                 S, (S <= 125) ? 1 : 2, d_ull + 8);       // TRACE_XOVR, align.h:45
         nrec = d2h(fam ? R.nrec_b : R.nrec_a, (size_t) n);
         int64_t total = 0;
         for (int i = 0; i < n; i++) total += nrec[i];
@@ -961,7 +961,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
     if (g_par.profile)
       out->prof = d2h(R.prof, (size_t) m->h_coff[n]);
     out->h2_events = (int64_t) d2h(d_ull + 6, 1)[0];
-    out->trace_fails = (int64_t) d2h(d_ull + 7, 1)[0];
+    out->trace_fails = (int64_t) d2h(d_ull + 8, 1)[0];
   }
 
   TRACE("report: copy out");

@@ -9,8 +9,39 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+_CAPMAN = None
+_FATAL_CB = None
+
+
 def pytest_configure(config):
+    global _CAPMAN
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+    _CAPMAN = config.pluginmanager.getplugin("capturemanager")
+
+
+def install_fatal_hook(api):
+    """The library reports fatal errors through the Clean_Exit callback (map.h:39) and then exits; under
+    pytest's capture that would end the run without a word.  The hook prints the message on the real
+    stderr before the process goes."""
+    import ctypes as C
+    global _FATAL_CB
+
+    def on_fatal(code):
+        try:
+            if _CAPMAN is not None:
+                _CAPMAN.suspend_global_capture(in_=True)
+        except Exception:
+            pass
+        try:
+            msg = api.load().damgpu_last_error().decode(errors="replace")
+        except Exception:
+            msg = "?"
+        sys.__stderr__.write("\n\nFATAL inside libdamgpu during a test (the process exits, code %d): %s\n" % (code, msg))
+        sys.__stderr__.flush()
+        os._exit(3)
+
+    _FATAL_CB = C.CFUNCTYPE(None, C.c_int)(on_fatal)
+    api.load().damgpu_set_fatal(C.cast(_FATAL_CB, C.c_void_p))
 
 
 def base_freq(contigs):

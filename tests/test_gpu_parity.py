@@ -16,7 +16,9 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 @pytest.fixture(scope="module")
 def api():
     from damapper_b200 import api as a
+    from conftest import install_fatal_hook
     a.init()          # raises without a B200: there is no fallback
+    install_fatal_hook(a)
     return a
 
 
