@@ -106,6 +106,45 @@ void cache_free(void *p)
   g_cached_bytes += it->second;
 }
 
+// ---- pool of page-locked host buffers (report.cuh: ByteVec) -------------------------------------
+static std::multimap<size_t, void *> g_pin_free;
+static std::unordered_map<void *, size_t> g_pin_size;     // 0 = plain malloc (page-locking failed)
+
+void *pinned_get(size_t bytes)
+{ if (bytes == 0) bytes = 1;
+  auto it = g_pin_free.lower_bound(bytes);
+  if (it != g_pin_free.end() && it->first <= 2 * bytes + (1u << 20))
+    { void *p = it->second;
+      g_pin_free.erase(it);
+      return p;
+    }
+  const size_t cap = (bytes + (1u << 20) - 1) & ~(size_t) ((1u << 20) - 1);
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) == cudaSuccess)
+    { g_pin_size[p] = cap;
+      return p;
+    }
+  cudaGetLastError();
+  p = malloc(cap);
+  if (p == nullptr)
+    fatal("out of host memory allocating %zu bytes", cap);
+  g_pin_size[p] = 0;
+  return p;
+}
+
+void pinned_put(void *p)
+{ if (p == nullptr) return;
+  auto it = g_pin_size.find(p);
+  if (it == g_pin_size.end())
+    fatal("pinned_put: unknown host pointer");
+  if (it->second == 0)
+    { free(p);
+      g_pin_size.erase(it);
+      return;
+    }
+  g_pin_free.emplace(it->second, p);
+}
+
 static void need_gpu()
 { if (!g_ready)
     { if (damgpu_init(-1) != 0)
@@ -466,7 +505,7 @@ int64_t damgpu_report_records(const damgpu_report *rr, int family)
 
 void damgpu_report_copy(const damgpu_report *rr, int family, uint8_t *out)
 { const ReportOut *r = reinterpret_cast<const ReportOut *>(rr);
-  const std::vector<uint8_t> &v = family == 0 ? r->a : family == 1 ? r->b : r->prof;
+  const ByteVec &v = family == 0 ? r->a : family == 1 ? r->b : r->prof;
   if (!v.empty()) memcpy(out, v.data(), v.size());
 }
 
@@ -480,7 +519,7 @@ void damgpu_report_stats(const damgpu_report *rr, int64_t out[8])
 int damgpu_report_write_las(const damgpu_report *rr, int family, const char *dir, const char *aname,
                             const char *bname, int nfiles, int tspace)
 { const ReportOut *r = reinterpret_cast<const ReportOut *>(rr);
-  const std::vector<uint8_t> &v = family == 0 ? r->a : r->b;
+  const ByteVec &v = family == 0 ? r->a : r->b;
   const std::vector<int64_t> &off = family == 0 ? r->read_off_a : r->read_off_b;
   const std::vector<int> &nrec = family == 0 ? r->read_nrec_a : r->read_nrec_b;
   if (off.empty()) return 1;

@@ -935,7 +935,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
       { const uint8_t *src = fam ? R.out_b : R.out_a;
         const int64_t *soff = fam ? d_outb_off : d_outa_off;
         const int64_t *used = fam ? R.used_b : R.used_a;
-        std::vector<uint8_t> &dstv = fam ? out->b : out->a;
+        ByteVec &dstv = fam ? out->b : out->a;
         std::vector<int64_t> &roff = fam ? out->read_off_b : out->read_off_a;
         std::vector<int>     &nrec = fam ? out->read_nrec_b : out->read_nrec_a;
         LAUNCH(k_scan_used, 1, 1024, 0, stream, used, n, d_off);
@@ -959,7 +959,10 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
       }
     dfree(d_off);
     if (g_par.profile)
-      out->prof = d2h(R.prof, (size_t) m->h_coff[n]);
+      { out->prof.resize((size_t) m->h_coff[n]);
+        if (!out->prof.empty())
+          CUDA_CHECK(cudaMemcpy(out->prof.data(), R.prof, out->prof.size(), cudaMemcpyDeviceToHost));
+      }
     out->h2_events = (int64_t) d2h(d_ull + 6, 1)[0];
     out->trace_fails = (int64_t) d2h(d_ull + 8, 1)[0];
   }
