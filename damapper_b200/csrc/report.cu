@@ -612,6 +612,28 @@ void build_align_spec(double ave_corr, const float freq[4], int *ave_path, int16
   set_table(0, 0, 0, 0, mscore, dscore, table, score);
 }
 
+// sizes of read r's slices in the second half of the Reporter: Ovl records, fusion trace scratch
+// (map.c:2129-2268 can fuse novl-1 pairs, each up to 5*(rlen/S)+16 values), output bytes of the
+// M and R families (40-byte records + trace bytes, fused traces included)
+__global__ void __launch_bounds__(256)
+k_read_sizes(int n, int S, int tb, const int32_t *__restrict__ rlen, const int *__restrict__ novl,
+             const int64_t *__restrict__ asum, const int64_t *__restrict__ bsum, int64_t *__restrict__ sz)
+{ const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int64_t no = novl[r];
+  const int64_t fus = (no > 1) ? (no - 1) * (5 * (rlen[r] / S) + 16) : 0;
+  sz[r] = no;
+  sz[(size_t) (n + 1) + r] = fus;
+  sz[2 * (size_t) (n + 1) + r] = 40ll * no + tb * (asum[r] + fus);
+  sz[3 * (size_t) (n + 1) + r] = 40ll * no + tb * (bsum[r] + fus);
+}
+
+__global__ void k_gather_totals(int n, const int64_t *a, const int64_t *b, const int64_t *c, const int64_t *d,
+                                int64_t *tot)
+{ if (threadIdx.x == 0)
+    { tot[0] = a[n]; tot[1] = b[n]; tot[2] = c[n]; tot[3] = d[n]; }
+}
+
 // exclusive scan of used[0..n) into off[0..n] (single CTA; n = reads of the block)
 __global__ void __launch_bounds__(1024) k_scan_used(const int64_t *__restrict__ used, int n, int64_t *off)
 { __shared__ int64_t part[1024];
@@ -880,20 +902,23 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   int     *d_novl = dalloc<int>(n + 1);
   int64_t *d_asum = dalloc<int64_t>(n + 1), *d_bsum = dalloc<int64_t>(n + 1);
   LAUNCH(k_read_totals, (n + 255) / 256, 256, 0, stream, n, d_job_off, d_jobs, d_alns, d_novl, d_asum, d_bsum);
-  std::vector<int> novl = d2h(d_novl, n);
-  std::vector<int64_t> asum = d2h(d_asum, n), bsum = d2h(d_bsum, n);
   const int tb = (S <= 125) ? 1 : 2;                   // TRACE_XOVR, align.h:21
-  std::vector<int64_t> ovl_off(n + 1), fus_off(n + 1), outa_off(n + 1), outb_off(n + 1);
-  int64_t to = 0, tf = 0, ta = 0, tbb = 0;
-  for (int i = 0; i < n; i++)
-    { ovl_off[i] = to; fus_off[i] = tf; outa_off[i] = ta; outb_off[i] = tbb;
-      const int64_t fus = (novl[i] > 1) ? (int64_t) (novl[i] - 1) * (5 * (rd->h_rlen[i] / S) + 16) : 0;
-      to += novl[i];
-      tf += fus;
-      ta += 40ll * novl[i] + tb * (asum[i] + fus);
-      tbb += 40ll * novl[i] + tb * (bsum[i] + fus);
-    }
-  ovl_off[n] = to; fus_off[n] = tf; outa_off[n] = ta; outb_off[n] = tbb;
+  // per-read capacities (records, fusion traces, output bytes of both families) and their exclusive
+  // scans stay on the device; only the four totals come back
+  int64_t *d_sz = dalloc<int64_t>((size_t) 4 * (n + 1));
+  int64_t *d_ovl_off = dalloc<int64_t>((size_t) n + 1), *d_fus_off = dalloc<int64_t>((size_t) n + 1);
+  int64_t *d_outa_off = dalloc<int64_t>((size_t) n + 1), *d_outb_off = dalloc<int64_t>((size_t) n + 1);
+  int64_t *d_tot = dalloc<int64_t>(4);
+  LAUNCH(k_read_sizes, (n + 255) / 256, 256, 0, stream, n, S, tb, rd->rlen, d_novl, d_asum, d_bsum, d_sz);
+  LAUNCH(k_scan_used, 1, 1024, 0, stream, d_sz, n, d_ovl_off);
+  LAUNCH(k_scan_used, 1, 1024, 0, stream, d_sz + (n + 1), n, d_fus_off);
+  LAUNCH(k_scan_used, 1, 1024, 0, stream, d_sz + 2 * (size_t) (n + 1), n, d_outa_off);
+  LAUNCH(k_scan_used, 1, 1024, 0, stream, d_sz + 3 * (size_t) (n + 1), n, d_outb_off);
+  LAUNCH(k_gather_totals, 1, 32, 0, stream, n, d_ovl_off, d_fus_off, d_outa_off, d_outb_off, d_tot);
+  int64_t h_tot[4] = { 0, 0, 0, 0 };
+  CUDA_CHECK(cudaMemcpyAsync(h_tot, d_tot, sizeof(h_tot), cudaMemcpyDeviceToHost, stream));
+  CUDA_CHECK(cudaStreamSynchronize(stream));
+  const int64_t to = h_tot[0], tf = h_tot[1], ta = h_tot[2], tbb = h_tot[3];
 
   ReportArgs R;
   memset(&R, 0, sizeof(R));
@@ -901,8 +926,6 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   R.small = (tb == 1); R.profile = g_par.profile; R.best_tie = g_par.best_tie;
   R.head = m->head; R.cand = m->cand; R.jobs = d_jobs; R.alns = d_alns;
   R.traces = d_traces; R.rlen = rd->rlen; R.cover = m->cover; R.coff = m->coff;
-  int64_t *d_ovl_off = h2d(ovl_off), *d_fus_off = h2d(fus_off), *d_outa_off = h2d(outa_off),
-          *d_outb_off = h2d(outb_off);
   R.job_off = d_job_off; R.ovl_off = d_ovl_off; R.fus_off = d_fus_off;
   R.outa_off = d_outa_off; R.outb_off = d_outb_off;
   R.ftraces = dalloc<uint16_t>((size_t) tf + 1);
@@ -972,7 +995,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   dfree(R.part); dfree(R.out_a); dfree(R.out_b); dfree(R.used_a); dfree(R.used_b);
   dfree(R.nrec_a); dfree(R.nrec_b); dfree(R.prof);
   dfree(d_ovl_off); dfree(d_fus_off); dfree(d_outa_off); dfree(d_outb_off);
-  dfree(d_novl); dfree(d_asum); dfree(d_bsum);
+  dfree(d_novl); dfree(d_asum); dfree(d_bsum); dfree(d_sz); dfree(d_tot);
   dfree(d_alns); dfree(d_traces); dfree(d_list); dfree(d_big);
   dfree(d_cells); dfree(d_tscr); dfree(d_ctr); dfree(d_ull);
   dfree(d_cell_base); dfree(d_lane_cells); dfree(d_unwind); dfree(d_lane_tscr);
