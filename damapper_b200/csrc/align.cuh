@@ -9,7 +9,10 @@ constexpr int ALIGN_WARPS = 4;            // warps (jobs in flight) per CTA
 #ifndef ALIGN_MINB
 #define ALIGN_MINB 5                      // resident CTAs per SM the register allocation aims at
 #endif
-constexpr int ALIGN_W     = 128;          // diagonal window in shared memory
+#ifndef ALIGN_W_V
+#define ALIGN_W_V 128
+#endif
+constexpr int ALIGN_W     = ALIGN_W_V;    // diagonal window in shared memory
 constexpr int ALIGN_W_BIG = 8192;         // diagonal window of the overflow kernel (global memory)
 #define ALIGN_STATE_BYTES(W) ((size_t) (W) * (2 * 8 + 10 * 4))
 constexpr int LANE_WARPS  = 4;            // lane kernel: warps per CTA, one CTA per SM
