@@ -127,8 +127,8 @@ damgpu_index  *damgpu_index_build(const damgpu_dblock *blk);               /* So
  * through the merge-join with one reference block's list (map.c:881-1002), where a record whose code
  * does not occur in the reference list contributes nothing.  The call records the block (which must
  * outlive the index); the first damgpu_mapper_match / damgpu_seeds_build / damgpu_Match_Filter
- * against a reference list extracts again with a membership test (hash bitmap of the reference codes
- * in both orientations), compacts in extraction order and sorts the survivors -- a sub-list of the
+ * against a reference list extracts again with a membership test (blocked Bloom filter of the reference
+ * codes in both orientations), compacts in extraction order and sorts the survivors -- a sub-list of the
  * reference's sorted list holding every record that can match, so run pairs, `gram` histogram and
  * seeds are identical.  The filtered list is reused for the complemented block.  With -t or masks, on
  * small blocks, or when the whole list is asked for (download / export / device_ptr, a third
