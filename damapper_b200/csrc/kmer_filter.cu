@@ -483,10 +483,11 @@ const KmerIndex *reads_view(const KmerIndex *ca, const KmerIndex *b, cudaStream_
       g_filter_times[0] = g_filter_times[1] = g_filter_times[2] = 0.f;
       return a->filt;
     }
-  // bitmap: ~32 bits per reference k-mer (two bits set per k-mer: 6 % of the bits at most).  In
-  // automatic mode it has to stay resident in L2 (2^29 bits = 64 MB): a lookup that goes to DRAM costs
-  // about what sorting the record costs, so a reference list that would fill more than 30 % of such a
-  // bitmap, or that is longer than 1.5x the reads list, gets the plain full sort.
+  // bitmap: ~32 bits per reference k-mer (four bits set per k-mer: two per orientation, 12 % of the
+  // bits at most).  In automatic mode it has to stay resident in L2 (2^29 bits = 64 MB): a lookup that
+  // goes to DRAM costs about what sorting the record costs, so a reference list that would fill more
+  // than 35 % of such a bitmap (12 % false positives), or that is longer than 1.5x the reads list, gets
+  // the plain full sort.
   int lg = g_filter_log2;
   if (lg == 0)
     { lg = 20;
@@ -496,7 +497,7 @@ const KmerIndex *reads_view(const KmerIndex *ca, const KmerIndex *b, cudaStream_
   if (lg < 10) lg = 10;
   if (lg > 32) lg = 32;
   if (g_filter_mode == 1 &&
-      (a->nfilt >= FILTER_MAX_BUILDS || 2.0 * b->len > 0.30 * (double) (1ll << lg) ||
+      (a->nfilt >= FILTER_MAX_BUILDS || 4.0 * b->len > 0.35 * (double) (1ll << lg) ||
        (double) b->len > 1.5 * (double) a->len))
     { dfree(sig);
       materialize_index(a, stream);

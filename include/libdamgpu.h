@@ -137,7 +137,7 @@ damgpu_index  *damgpu_index_build(const damgpu_dblock *blk);               /* So
 damgpu_index  *damgpu_index_build_deferred(const damgpu_dblock *blk);
 int            damgpu_index_is_deferred(const damgpu_index *idx);
 /* mode 0 = never filter, 1 = automatic (default: filter when the reads block has >= 4 M k-mers, the
- * reference list is at most 1.5x as long and fills at most 30 % of a bitmap that stays in L2 (64 MB),
+ * reference list is at most 1.5x as long and fills at most 35 % of a bitmap that stays in L2 (64 MB),
  * and for at most two reference blocks per reads block), 2 = always; log2_bits = size of the bitmap
  * (0 = 32 bits per reference k-mer).  Environment: DAMGPU_FILTER=off|auto|always, DAMGPU_FILTER_BITS */
 void           damgpu_set_reads_filter(int mode, int log2_bits);
