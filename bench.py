@@ -378,7 +378,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "reads_per_gpu": int(hr.nreads), "read_bases_per_gpu": bases,
-                       "kmer": 20, "l2": "inputs larger than L2: the reads k-mer list is %.1f GB" % (16.0 * n / 1e9),
+                       "kmer": 20, "l2": "inputs larger than L2 (126 MB): the reads block is %.0f MB (1 byte per base), the whole k-mer "
+                             "list sorted in the roofline region %.1f GB; no flush between steps" % (bases / 1e6, 16.0 * n / 1e9),
                        "index": "built on rank 0 and broadcast with NCCL" if world > 1 else "built locally"},
             "e2e": {"value": total_bases / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
