@@ -15,11 +15,9 @@ constexpr int ALIGN_WARPS = 4;            // warps (jobs in flight) per CTA
 constexpr int ALIGN_W     = ALIGN_W_V;    // diagonal window in shared memory
 constexpr int ALIGN_W_BIG = 8192;         // diagonal window of the overflow kernel (global memory)
 #define ALIGN_STATE_BYTES(W) ((size_t) (W) * (2 * 8 + 10 * 4))
-constexpr int LANE_WARPS  = 4;            // lane kernel: warps per CTA, one CTA per SM
-constexpr int LANE_W      = 64;           // lane kernel: diagonal window per lane (shared memory)
-constexpr int LANE_WIN    = 32;           // lane kernel: words of each per-lane sequence window
-#define LANE_WARP_WORDS(dob) ((((dob) ? 6 : 5) * LANE_W + 2 * LANE_WIN + 20) * 32)
-#define LANE_ARENA(tps) (16 * (tps) + 512)   // Pebble cells per job, tps = read length / spacing
+constexpr int DUO_WARPS   = 4;            // duo kernel: warps per CTA (two jobs each)
+constexpr int DUO_W       = 32;           // duo kernel: diagonal window of a half in wide mode
+#define LANE_ARENA(tps) (16 * (tps) + 512)   // duo kernel: Pebble cells per job, tps = read length / spacing
 
 // What the waves need of _Align_Spec (align.c:183-191); tables built on the host (align.c:207-269)
 struct AlignSpecD
@@ -39,12 +37,7 @@ struct AlnRec
   long long atrace, btrace;               // offsets into the uint16 trace pool
 };
 
-constexpr int PACK_WARPS  = 4;            // packed kernel: warps per CTA
-constexpr int PACK_W      = 64;           // packed kernel: diagonal window per slot (shared memory)
-#define PACK_SLOT_WORDS(dob) (((dob) ? 10 : 9) * PACK_W + 8)       /* +8: slots start 8 banks apart */
-#define PACK_WARP_WORDS(g, dob) ((g) * 16 + (g) * PACK_SLOT_WORDS(dob))
-
-// Lane kernel (align_lane.cu): what k_unwind needs of one wave call, and the calls whose traces
+// Duo kernel (align_duo.cu): what k_unwind needs of one wave call, and the calls whose traces
 // make up one kept alignment (forward then reverse; a DUB_TRIM re-run stands alone).
 struct LaneCall
 { long long cells;                        // first Pebble of the call in the arena
@@ -83,7 +76,7 @@ struct AlignArgs
   uint16_t        *traces; unsigned long long *trace_top; long long trace_cap;
   int             *nfailed;
   unsigned long long *stats;              // nalign, nwaves, ncells, empty-band events
-  // lane kernel
+  // duo kernel
   void            *lane_cells;            // Pebble arena: per job 8*(rlen/spacing)+256 cells
   const long long *lane_cell_base;        // per read: arena index of its first job
   const int64_t   *lane_job_off;          // per read: index of its first job
@@ -92,10 +85,7 @@ struct AlignArgs
 };
 
 void launch_align(const AlignArgs &A, bool big, int nblocks, cudaStream_t stream);
-void launch_align_pack(const AlignArgs &A, int njobs, cudaStream_t stream);
-void launch_align_group(const AlignArgs &A, int njobs, cudaStream_t stream);
-int  lane_warps(bool dob);
-void launch_align_lane(const AlignArgs &A, int nblocks, cudaStream_t stream);
+void launch_align_duo(const AlignArgs &A, int njobs, cudaStream_t stream);
 void launch_unwind(const AlignArgs &A, int max_alns, cudaStream_t stream);
 
 }  // namespace damgpu

@@ -27,7 +27,7 @@ static float       g_sort_times[3] = { 0, 0, 0 };
 Params g_par;          // filter parameters + the map.h globals
 bool   g_trace = false;
 bool   g_debug_sync = false;
-int    g_align_tier = 0, g_align_slots = 4;
+int    g_align_tier = 1, g_align_slots = 2;
 bool   g_chain_async = true;
 
 void trace_mark(const char *name)
@@ -189,10 +189,8 @@ int damgpu_init(int device)
   g_trace = (getenv("DAMGPU_TRACE") != nullptr);
   g_debug_sync = (getenv("DAMGPU_DEBUG_SYNC") != nullptr);
   if (const char *t = getenv("DAMGPU_ALIGN"))
-    g_align_tier = !strcmp(t, "warp") ? 0 : !strcmp(t, "lane") ? 1 : !strcmp(t, "group") ? 3 : 2;
+    g_align_tier = !strcmp(t, "warp") ? 0 : 1;
   g_chain_async = (getenv("DAMGPU_SYNC_CHAIN") == nullptr);
-  if (const char *t = getenv("DAMGPU_SLOTS"))
-    g_align_slots = atoi(t);
   if (const char *t = getenv("DAMGPU_RADIX"))
     g_radix_reload = !strcmp(t, "reload");
   g_radix_pf = g_sms;                                    // one tile per SM ahead (flat between 64 and 200 on B200)
@@ -226,8 +224,8 @@ int damgpu_device_memory(uint64_t *free_bytes, uint64_t *total_bytes)
 }
 void damgpu_time_kernels(int on) { g_time_kernels = (on != 0); }
 void damgpu_set_align_tier(int tier, int slots)
-{ g_align_tier = (tier < 0 || tier > 3) ? 0 : tier;
-  g_align_slots = (slots == 2 || slots == 8) ? slots : 4;
+{ g_align_tier = (tier == 0) ? 0 : 1;
+  (void) slots;
 }
 void damgpu_last_join_times(float out[4]) { join_times(out); }
 void damgpu_last_sort_times(float out[3]) { out[0] = g_sort_times[0]; out[1] = g_sort_times[1]; out[2] = g_sort_times[2]; }

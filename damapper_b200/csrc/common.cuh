@@ -60,9 +60,8 @@ int sm_count();
 void trace_mark(const char *name);
 #define TRACE(name) do { if (damgpu::g_trace) damgpu::trace_mark(name); } while (0)
 extern bool g_trace;
-// first tier of the alignment phase: 0 = warp per job (align.cu), 1 = thread per job
-// (align_lane.cu), 2 = several jobs per warp, diagonals packed onto the lanes (align_pack.cu).
-// DAMGPU_ALIGN=warp|lane|pack and DAMGPU_SLOTS=2|4|8 override (development).
+// first tier of the alignment phase: 1 = two jobs per warp (align_duo.cu, default), 0 = warp per
+// job (align.cu, also the tier that re-runs what outgrows the first).  DAMGPU_ALIGN=warp|duo.
 extern int g_align_tier, g_align_slots;
 extern bool g_chain_async;         // chain kernel on its own stream (DAMGPU_SYNC_CHAIN=1 turns it off)
 

@@ -784,7 +784,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   AlnRec   *d_alns = dalloc<AlnRec>((size_t) aln_cap);
   uint16_t *d_traces = dalloc<uint16_t>((size_t) trace_cap);
 
-  // lane kernel (first tier): per-job Pebble arenas, unwind records, trace scratch per record
+  // duo kernel (first tier): per-job Pebble arenas, unwind records, trace scratch per record
   std::vector<long long> cell_base(n + 1);
   long long ncell = 0;
   for (int i = 0; i < n; i++)
@@ -820,18 +820,8 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   if (g_time_kernels)
     { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, stream); }
   if (njobs > 0)
-    { if (g_align_tier == 3)
-        { launch_align_group(A, njobs, stream);
-          launch_unwind(A, aln_cap, stream);
-        }
-      else if (g_align_tier == 2)
-        { launch_align_pack(A, njobs, stream);
-          launch_unwind(A, aln_cap, stream);
-        }
-      else if (g_align_tier == 1)
-        { const int lpb = lane_warps(do_b != 0) * 32;
-          const int lblocks = std::min((njobs + lpb - 1) / lpb, sm_count());
-          launch_align_lane(A, lblocks, stream);
+    { if (g_align_tier != 0)
+        { launch_align_duo(A, njobs, stream);
           launch_unwind(A, aln_cap, stream);
         }
       else
@@ -894,7 +884,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
     fprintf(stderr, "[trace] longest job: %llu waves in %llu alignments; mean %.0f waves per job\n",
             stats[7] >> 20, stats[7] & 0xfffff, njobs ? (double) stats[2] / njobs : 0.);
   if (g_trace && stats[5] != 0)
-    fprintf(stderr, "[trace] lane kernel hand-offs: band %llu, cells %llu, trace %llu, other %llu\n",
+    fprintf(stderr, "[trace] duo kernel hand-offs: band %llu, cells %llu, trace %llu, other %llu\n",
             stats[5] & 0xffff, (stats[5] >> 16) & 0xffff, (stats[5] >> 32) & 0xffff, stats[5] >> 48);
 
   TRACE("report: overflow loop");

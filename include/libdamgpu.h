@@ -83,10 +83,9 @@ uint64_t damgpu_launch_count(void);                   /* kernels launched so far
  * (the reference sizes its working set from physical memory the same way, damapper.c:74-141) */
 int  damgpu_device_memory(uint64_t *free_bytes, uint64_t *total_bytes);
 void damgpu_time_kernels(int on);                     /* record per-phase CUDA-event times  */
-/* first tier of the alignment phase: 0 = warp per candidate (default), 1 = thread per candidate,
-   2 = `slots` candidates per warp with their diagonals packed onto the lanes (slots 2, 4 or 8),
-   3 = `slots` candidates per warp, each owned by a fixed group of 32/slots lanes;
-   every tier yields the same records (Local_Alignment, align.c:1727-1946) */
+/* first tier of the alignment phase: 1 = two candidates per warp, one per 16-lane half (default),
+   0 = a warp per candidate (the tier that also re-runs what outgrows the first); `slots` is
+   ignored; both yield the same records (Local_Alignment, align.c:1727-1946) */
 void damgpu_set_align_tier(int tier, int slots);
 /* ms of the last Sort_Kmers: [0]=extraction kernel, [1]=all radix passes, [2]=#passes */
 void damgpu_last_sort_times(float out[3]);
