@@ -110,12 +110,13 @@ __device__ __forceinline__ int slide2(const uint32_t *__restrict__ aw, const uin
 // M of the reference for an inverted history word
 __device__ __forceinline__ int hist_m(uint64_t t) { return PATH_LEN + 1 - __popcll(t & HIST61); }
 
-// the trim test of align.c:824-826 on an inverted history word
-__device__ __forceinline__ bool trim_ok(uint64_t t, const AlignSpecD &sp)
+// the trim test of align.c:824-826 on an inverted history word; sc0 = score[0]: the score table is
+// 1000 popc(p) + score[0] (set_table, align.c:199-213: mscore + dscore = FRACTION)
+__device__ __forceinline__ bool trim_ok(uint64_t t, const AlignSpecD &sp, int sc0)
 { const uint32_t b = ~(uint32_t) t;
   const int lo15 = (int) (b & TRIM_MASK), hi15 = (int) ((b >> TRIM_LEN) & TRIM_MASK);
   if (__ldg(sp.table + lo15) < 0) return false;
-  return (__ldg(sp.table + hi15) + __ldg(sp.score + lo15) >= 0);
+  return (__ldg(sp.table + hi15) + 1000 * __popc(lo15) + sc0 >= 0);
 }
 
 // how many trace coordinates n, n+TS, .. the point p has reached, and how many of those the
@@ -136,7 +137,7 @@ __device__ __forceinline__ void crossings(int p, int n, int mk, int TS, int &cnt
 // ---- the scalar side: lane 0 of a half advances its control record until a wave call is ready
 // to run (PH_WAVE) or there is no more work (PH_DONE) --------------------------------------------
 template <bool DOB>
-__device__ __noinline__ void duo_control(DuoCtl &C, const AlignArgs &A)
+__device__ __forceinline__ void duo_control(DuoCtl &C, const AlignArgs &A)
 { const int TS = A.spec.spacing;
   const int hithr = 3 * A.kmer;                           // HITMIN*Kmer, map.c:2419
   LPebble *const arena = reinterpret_cast<LPebble *>(A.lane_cells);
@@ -371,14 +372,23 @@ __device__ __noinline__ void duo_control(DuoCtl &C, const AlignArgs &A)
 #ifndef DUO_MINB
 #define DUO_MINB 5
 #endif
+#ifdef DUO_DEBUG_DIV
+__device__ unsigned long long g_duo_dbg[64];
+#define DBG_EV(b) (dbg_ev |= (b))
+#define DBG_CP(i) do { if (__activemask() != FULL && lead) atomicAdd(&g_duo_dbg[56 + (i)], 1ull); } while (0)
+#else
+#define DBG_EV(b)
+#define DBG_CP(i)
+#endif
 
 template <bool DOB>
 __global__ void __launch_bounds__(DUO_WARPS * 32, DUO_MINB)
 k_align_duo(const __grid_constant__ AlignArgs A)
 { extern __shared__ __align__(16) unsigned char dsm[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int half = lane >> 4, hl = lane & 15, hsh = half * 16;
-  const unsigned hmask = 0xffffu << hsh;
+  const int half = lane >> 4, hl = lane & 15;
+  const unsigned hmask = 0xffffu << (half * 16);
+  const unsigned dupsel = half ? 0x3232u : 0x1010u;       // PRMT selector: own ballot half, twice
   const bool lead = (hl == 0);
   DuoCtl &C = reinterpret_cast<DuoCtl *>(dsm)[wib * 2 + half];
   int *const win = reinterpret_cast<int *>(dsm + sizeof(DuoCtl) * 2 * DUO_WARPS)
@@ -387,15 +397,19 @@ k_align_duo(const __grid_constant__ AlignArgs A)
 #define WNA(k)      win[(2 * F_INH) * DUO_W + ((k) & (DUO_W - 1))]
 #define WNB(k)      win[(2 * F_INH + 1) * DUO_W + ((k) & (DUO_W - 1))]
 #define SHF(v, l)   __shfl_sync(FULL, (v), (l), 16)
-#define MY16(b)     (((b) >> hsh) & 0xffffu)
-  // bits of a half's ballot in scan order: bit i <-> diagonal kh - i (lane (s + i) & 15)
-#define SCAN16(b)   ((((b) | ((b) << 16)) >> s) & 0xffffu)
+  // a half's 16 ballot bits, duplicated into both halves of a word
+#define DUP16(b)    __byte_perm((b), 0u, dupsel)
+#define MY16(b)     (DUP16(b) & 0xffffu)
+  // ... rotated into scan order: bits i and i+16 <-> diagonal kh - i (lane (s + i) & 15).  The lowest
+  // scan index set is __ffs(x) - 1, the highest 15 - __clz(x).
+#define ROT16(b)    __funnelshift_r(DUP16(b), DUP16(b), s)
 
   const int TS = A.spec.spacing;
   const int mgood = PATH_LEN + 1 - A.spec.ave_path;       // m >= PATH_AVE <=> popcount <= mgood
+  const int sc0 = __ldg(A.spec.score);                    // score[p] = 1000 popc(p) + score[0] (align.c:199-213)
   LPebble *const arena = reinterpret_cast<LPebble *>(A.lane_cells);
 
-  // per-diagonal state of lane's diagonal (narrow mode)
+  // per-diagonal state of the lane's diagonal (narrow mode)
   int rV = NEG, rHA = 0, rHB = 0, rNA = 0, rNB = 0, rMA = 0, rMB = 0;
   uint64_t rT = 0;
   // captured by the lane that produced them
@@ -406,8 +420,11 @@ k_align_duo(const __grid_constant__ AlignArgs A)
   int dir = 1, asd = 0, bsd = 0, aend = 0, bend = 0;
   const uint32_t *aw = nullptr, *bw = nullptr;
   LPebble *cells = nullptr;
-  unsigned nwaves = 0, ncells = 0;
+  unsigned ncells = 0;
   bool waving = false, wide = false, done = false;
+#ifdef DUO_DEBUG_DIV
+  unsigned dbg_ev = 0; bool dbg_split = false;
+#endif
 
   if (lead)
     { C.phase = PH_IDLE;
@@ -416,430 +433,467 @@ k_align_duo(const __grid_constant__ AlignArgs A)
   __syncwarp();
 
   while (true)
-    { // ---- control: a half that is not inside a wave call lets its lane 0 run the state machine
-      if (!waving && !done)
-        { if (lead) duo_control<DOB>(C, A);
-          __syncwarp(hmask);
-          if (C.phase == PH_DONE)
-            done = true;
-          else
-            { dir = C.dir; asd = C.asd; bsd = C.bsd; aend = C.aend; bend = C.bend;
-              aw = C.aw; bw = C.bw;
-              cells = arena + C.abase + C.cbase; cellcap = C.cellcap;
-              low = C.low; hgh = C.hgh; more = C.more; besta = C.besta; lasta = C.lasta;
-              avail = C.avail; dif = 0; trimd = 0; status = 0;
-              tC = C.trima; tY = C.trimy; tHA = C.trimha; tHB = C.trimhb; bY = C.besty;
-              tlane = 0; blane = 0;                      // every lane holds the wave-0 values
-              if (((-C.k0) & 15) == hl)                   // the one diagonal of wave 0
-                { rV = C.v0; rT = HIST0; rHA = C.ha0; rHB = C.hb0; rNA = C.na0; rNB = C.nb0;
-                  rMA = C.ma0; rMB = C.mb0;
-                }
-              nwaves = 0; ncells = 0;
-              waving = true; wide = false; cur = 0;
-            }
-          __syncwarp(hmask);
-        }
-      if (__all_sync(FULL, done))
-        break;
-
-      // ---- top of a wave (align.c:592 / 1248): go on?
-      bool go = waving;
-      if (waving)
-        { go = (more != 0) && (lasta >= besta - TRIM_MLAG) && (status == 0);
-          if (go && hgh < low)                            // empty band: the reference would read
-            { if (lead) C.nempty += 1;                    // stale cells; stop (as align.cu does)
-              go = false;
-            }
-          if (go && hgh - low + 3 > DUO_W)
-            { status = DERR_BAND; go = false; }
-        }
-      const bool ending = waving && !go;
-      if (__any_sync(FULL, ending))
-        { const int xC = SHF(tC, tlane), xY = SHF(tY, tlane), xHA = SHF(tHA, tlane), xHB = SHF(tHB, tlane);
-          if (ending)
-            { if (lead)
-                { C.trima = xC; C.trimy = xY; C.trimd = trimd; C.trimha = xHA; C.trimhb = xHB;
-                  C.avail = avail;
-                  C.nwaves += nwaves; C.ncells += ncells;
-                  if (status != 0) { C.status = status; C.phase = PH_JOBEND; }
-                  else             C.phase = PH_ENDCALL;
-                }
-              waving = false;
-            }
-          __syncwarp();
-          continue;
-        }
-
-      // ---- registers <-> window when the next wave needs more / no more than 16 lanes
-      { const int wnext = hgh - low + 3;
-        const bool spill = go && !wide && wnext > 16, fill = go && wide && wnext <= 16;
-        if (__any_sync(FULL, spill || fill))
-          { const int s0 = (-hgh) & 15, r0 = (hl - s0) & 15, k = hgh - r0;
-            const bool have = (r0 < hgh - low + 1);
-            if (spill)
-              { if (have)
-                  { WF(F_V, 0, k) = rV; WF(F_TL, 0, k) = (int) (uint32_t) rT; WF(F_TH, 0, k) = (int) (uint32_t) (rT >> 32);
-                    WF(F_HA, 0, k) = rHA; WF(F_HB, 0, k) = rHB; WF(F_MA, 0, k) = rMA; WF(F_MB, 0, k) = rMB;
-                    WNA(k) = rNA; WNB(k) = rNB;
-                  }
-                cur = 0; wide = true;
-              }
-            __syncwarp();
-            if (fill)
-              { if (have)
-                  { rV = WF(F_V, cur, k);
-                    rT = ((uint64_t) (uint32_t) WF(F_TH, cur, k) << 32) | (uint32_t) WF(F_TL, cur, k);
-                    rHA = WF(F_HA, cur, k); rHB = WF(F_HB, cur, k); rMA = WF(F_MA, cur, k); rMB = WF(F_MB, cur, k);
-                    rNA = WNA(k); rNB = WNB(k);
-                  }
-                wide = false;
-              }
-            __syncwarp();
-          }
+    { bool nar;
+      // The two halves must run every wave as ONE warp.  Divergence the compiler does not expect (a half
+      // waiting for the other's lane 0 in the control section) leaves two thread groups that leapfrog
+      // through the same code, each sync instruction taking its slow collective path and every
+      // instruction issuing twice (measured: 17 active threads per instruction, 22 ms instead of 6).
+      // Groups merge when both are runnable at the same instruction; a YIELD at the loop head makes the
+      // group that arrives first let the other catch up.  There is no intrinsic for YIELD: the
+      // compiler emits one at the head of a loop that contains a volatile load (a possible spin wait).
+      { const int yield_ = *reinterpret_cast<volatile int *>(&C.phase); (void) yield_; }
+#ifdef DUO_DEBUG_DIV
+      { const bool split = (__activemask() != FULL);
+        if (lead) atomicAdd(&g_duo_dbg[split ? 1 : 0], 1ull);
+        if (split && !dbg_split && lead) atomicAdd(&g_duo_dbg[8 + (dbg_ev & 31)], 1ull);
+        if (!split && dbg_split && lead) atomicAdd(&g_duo_dbg[40 + (dbg_ev & 15)], 1ull);
+        dbg_split = split; dbg_ev = 0;
       }
-
-      // =================================== narrow wave: one diagonal per lane, state in registers
-      const bool nar = go && !wide;
-      if (__any_sync(FULL, nar))
-        { if (nar) { low -= 1; hgh += 1; dif += 1; }
-          const int kh = hgh;                             // lane mapping of this wave
-          const int s = (-kh) & 15, r = (hl - s) & 15, k = kh - r;
-          const int width = hgh - low + 1;
-          const bool act = nar && (r < width);
-          // new outer diagonals inherit NA/NB from their inner neighbour (align.c:678-690)
-          { const bool outer = act && (r == 0 || r == width - 1);
-            const int inner = (r == 0) ? hl + 1 : hl - 1;
-            const int nai = SHF(rNA, inner);
-            if (outer) rNA = nai;
-            if (DOB)
-              { const int nbi = SHF(rNB, inner);
-                if (outer) rNB = nbi;
+#endif
+      { const bool go = waving && (more != 0) && (lasta >= besta - TRIM_MLAG) && (status == 0) && (hgh >= low);
+        nar = go && !wide && (hgh - low + 3 <= 16);
+      }
+      if (!__all_sync(FULL, nar))
+        { // =========== everything that is not "both halves run a narrow wave" ===========
+          // ---- a wave call ends (align.c:592 / 1248)
+          { bool go = waving && (more != 0) && (lasta >= besta - TRIM_MLAG) && (status == 0);
+            if (go && hgh < low)                          // empty band: the reference would read
+              { if (lead) C.nempty += 1;                  // stale cells; stop (as align.cu does)
+                go = false;
               }
-          }
-          const int vold = (act && r > 0 && r < width - 1) ? rV : NEG;
-          const int vp = SHF(vold, hl - 1), vn = SHF(vold, hl + 1);     // diagonals k+1, k-1
-          int c, srcl;
-          if (vold < vn)                                  // align.c:712-741 / 1367-1396
-            { if (vn < vp) { c = vp + 1; srcl = hl - 1; }
-              else         { c = vn + 1; srcl = hl + 1; }
-            }
-          else
-            { if (vold < vp) { c = vp + 1; srcl = hl - 1; }
-              else           { c = vold + 2; srcl = hl; }
-            }
-          uint64_t t;
-          { const unsigned tl = SHF((unsigned) rT, srcl), th = SHF((unsigned) (rT >> 32), srcl);
-            t = ((uint64_t) th << 32) | tl;
-          }
-          int ha = SHF(rHA, srcl), ma = SHF(rMA, srcl), hb = 0, mb = 0;
-          if (DOB) { hb = SHF(rHB, srcl); mb = SHF(rMB, srcl); }
-          int y = 0, hit = 0, cntA = 0, skipA = 0, cntB = 0, skipB = 0;
-          if (act)
-            { t = (t << 1) | 1ull;                         // the difference
-              const int y0 = (c - k) >> 1;
-              y = slide2(aw, bw, asd, bsd, dir, aend, bend, k, y0, hit);
-              const int run = y - y0;
-              t = (run >= 64) ? 0ull : (t << run);         // matches
-              c = (y << 1) + k;
-              crossings(y + k, rNA, ma, TS, cntA, skipA);  // align.c:771-793 / 1426-1448
-              if (DOB) crossings(y, rNB, mb, TS, cntB, skipB);   // align.c:795-817 / 1449-1471
-            }
-          else
-            c = NEG;
-
-          // Pebble cells: numbered by ballot rank, one A and one B cell per lane and round
-          { int remA = cntA - skipA, remB = cntB - skipB;
-            int nxA = rNA + TS * skipA, nxB = rNB + TS * skipB;
-            unsigned pa = __ballot_sync(FULL, remA > 0), pb = __ballot_sync(FULL, remB > 0);
-            while (pa | pb)
-              { const unsigned a16 = MY16(pa), b16 = MY16(pb), lt = (1u << hl) - 1;
-                const int na_ = __popc(a16), tot = na_ + __popc(b16);
-                if (avail + tot > cellcap)
-                  { if (tot) status = DERR_CELLS;
-                    remA = remB = 0;
-                  }
-                else
-                  { if (remA > 0)
-                      { const int ix = avail + __popc(a16 & lt);
-                        cells[ix] = LPebble{ ha, dir * k, dif, dir * nxA };
-                        ha = ix; ma = nxA; nxA += TS; remA -= 1;
+            if (go && hgh - low + 3 > DUO_W)
+              { status = DERR_BAND; go = false; }
+            const bool ending = waving && !go;
+            if (__any_sync(FULL, ending))
+              { DBG_EV(1);
+                const int xC = SHF(tC, tlane), xY = SHF(tY, tlane), xHA = SHF(tHA, tlane), xHB = SHF(tHB, tlane);
+                if (ending)
+                  { if (lead)
+                      { C.trima = xC; C.trimy = xY; C.trimd = trimd; C.trimha = xHA; C.trimhb = xHB;
+                        C.avail = avail;
+                        C.nwaves += (unsigned) dif; C.ncells += ncells;
+                        if (status != 0) { C.status = status; C.phase = PH_JOBEND; }
+                        else             C.phase = PH_ENDCALL;
                       }
-                    if (remB > 0)
-                      { const int ix = avail + na_ + __popc(b16 & lt);
-                        cells[ix] = LPebble{ hb, dir * k, dif, dir * nxB };
-                        hb = ix; mb = nxB; nxB += TS; remB -= 1;
+                    waving = false;
+                  }
+                __syncwarp();
+              }
+          }
+          // ---- control: a half that is not inside a wave call lets its lane 0 run the state machine
+          // (all 32 lanes walk through here together: every warp-level sync stays full-mask)
+          { const bool ctl = !waving && !done;
+            if (__any_sync(FULL, ctl))
+              { DBG_EV(2);
+                if (ctl && lead) duo_control<DOB>(C, A);
+                __syncwarp();
+                if (ctl)
+                  { if (C.phase == PH_DONE)
+                      done = true;
+                    else
+                      { dir = C.dir; asd = C.asd; bsd = C.bsd; aend = C.aend; bend = C.bend;
+                        aw = C.aw; bw = C.bw;
+                        cells = arena + C.abase + C.cbase; cellcap = C.cellcap;
+                        low = C.low; hgh = C.hgh; more = C.more; besta = C.besta; lasta = C.lasta;
+                        avail = C.avail; dif = 0; trimd = 0; status = 0;
+                        tC = C.trima; tY = C.trimy; tHA = C.trimha; tHB = C.trimhb; bY = C.besty;
+                        tlane = 0; blane = 0;             // every lane holds the wave-0 values
+                        if (((-C.k0) & 15) == hl)         // the one diagonal of wave 0
+                          { rV = C.v0; rT = HIST0; rHA = C.ha0; rHB = C.hb0; rNA = C.na0; rNB = C.nb0;
+                            rMA = C.ma0; rMB = C.mb0;
+                          }
+                        ncells = 0;
+                        waving = true; wide = false; cur = 0;
                       }
-                    avail += tot;
                   }
-                pa = __ballot_sync(FULL, remA > 0); pb = __ballot_sync(FULL, remB > 0);
+                __syncwarp();
               }
           }
-          if (act)
-            { rNA += TS * cntA; rV = c; rT = t; rHA = ha; rMA = ma;
-              if (DOB) { rNB += TS * cntB; rHB = hb; rMB = mb; }
-            }
+          if (__all_sync(FULL, done))
+            break;
+          const bool go = waving && (more != 0) && (lasta >= besta - TRIM_MLAG) && (status == 0) && (hgh >= low)
+                          && (hgh - low + 3 <= DUO_W);
 
-          // record breakers in scan order (align.c:819-833 / 1473-1487): running maximum over the
-          // points beyond besta, walked in scan order (seldom more than two or three)
-          { const unsigned cb = __ballot_sync(FULL, c > besta);
-            unsigned rest = SCAN16(MY16(cb)), brk = 0;
-            int rm = besta;
-            while (__any_sync(FULL, rest != 0))
-              { const int i = __ffs(rest) - 1;
-                const int v = SHF(c, s + i);
-                if (rest != 0 && v > rm) { rm = v; brk |= 1u << i; }
-                rest &= rest - 1;
-              }
-            const bool isb = act && ((brk >> r) & 1u);
-            const bool good = isb && (__popcll(t & HIST61) <= mgood);
-            const bool trim = good && trim_ok(t, A.spec);
-            const unsigned gb = __ballot_sync(FULL, good), tb = __ballot_sync(FULL, trim);
-            const unsigned gs = SCAN16(MY16(gb)), ts = SCAN16(MY16(tb));
-            const int gl = s + 31 - __clz(gs);             // lane (mod 16) of the last good breaker
-            const int cg = SHF(c, gl);
-            if (brk)
-              { besta = rm;
-                blane = (s + 31 - __clz(brk)) & 15;
-                if (hl == blane) bY = y;
-                if (gs) lasta = cg;
-                if (ts)
-                  { tlane = (s + 31 - __clz(ts)) & 15;
-                    trimd = dif;
-                    if (hl == tlane) { tC = c; tY = y; tHA = ha; tHB = hb; }
+          // ---- registers <-> window when the next wave needs more / no more than 16 lanes
+          { const int wnext = hgh - low + 3;
+            const bool spill = go && !wide && wnext > 16, fill = go && wide && wnext <= 16;
+            if (__any_sync(FULL, spill || fill))
+              { DBG_EV(4);
+                const int s0 = (-hgh) & 15, r0 = (hl - s0) & 15, k = hgh - r0;
+                const bool have = (r0 < hgh - low + 1);
+                if (spill)
+                  { if (have)
+                      { WF(F_V, 0, k) = rV; WF(F_TL, 0, k) = (int) (uint32_t) rT; WF(F_TH, 0, k) = (int) (uint32_t) (rT >> 32);
+                        WF(F_HA, 0, k) = rHA; WF(F_HB, 0, k) = rHB; WF(F_MA, 0, k) = rMA; WF(F_MB, 0, k) = rMB;
+                        WNA(k) = rNA; WNB(k) = rNB;
+                      }
+                    cur = 0; wide = true;
                   }
+                __syncwarp();
+                if (fill)
+                  { if (have)
+                      { rV = WF(F_V, cur, k);
+                        rT = ((uint64_t) (uint32_t) WF(F_TH, cur, k) << 32) | (uint32_t) WF(F_TL, cur, k);
+                        rHA = WF(F_HA, cur, k); rHB = WF(F_HB, cur, k); rMA = WF(F_MA, cur, k); rMB = WF(F_MB, cur, k);
+                        rNA = WNA(k); rNB = WNB(k);
+                      }
+                    wide = false;
+                  }
+                __syncwarp();
               }
           }
 
-          // sequence ends (align.c:752-763,848-875 / 1407-1418,1502-1529)
-          if (__ballot_sync(FULL, act && hit != 0))
-            { const unsigned ab = __ballot_sync(FULL, act && hit == 2), bb = __ballot_sync(FULL, act && hit == 1);
-              const unsigned as_ = SCAN16(MY16(ab)), bs_ = SCAN16(MY16(bb));
-              int aclip = IMAX, bclip = -IMAX;
-              if (as_ | bs_) more = 0;
-              if (as_) aclip = kh - (31 - __clz(as_));     // last writer in scan order
-              if (bs_) bclip = kh - (__ffs(bs_) - 1);      // extreme k towards the scan start
-              const bool clip = nar && (more == 0);
-              const int yb = SHF(bY, blane);
-              const int la = (-aclip) & 15, lb = (-bclip) & 15;
-              const int mloc = hist_m(rT), morem0 = C.morem, alo = C.alo, blo = C.blo;
+          // ---- wide wave: 17..32 diagonals, state in the window, 16 at a time
+          const bool wid = go && wide;
+          if (__any_sync(FULL, wid))
+            { DBG_EV(8);
+              if (wid) { low -= 1; hgh += 1; dif += 1; }
+              const int kh = hgh, kl = low;
+              const int width = wid ? hgh - low + 1 : 0;
+              const int nxt = cur ^ 1;
+              if (wid && lead)
+                { WNA(kl) = WNA(kl + 1); WNA(kh) = WNA(kh - 1);
+                  if (DOB) { WNB(kl) = WNB(kl + 1); WNB(kh) = WNB(kh - 1); }
+                }
               __syncwarp();
-              const int am = SHF(mloc, la), av = SHF(rV, la), aha = SHF(rHA, la), ahb = SHF(rHB, la);
-              const int bm = SHF(mloc, lb), bv = SHF(rV, lb), bha = SHF(rHA, lb), bhb = SHF(rHB, lb);
-              if (clip)
-                { const int xb = besta - yb;
-                  if (yb >= blo && yb < bend && xb >= alo && xb < aend)
+              int aclip = IMAX, bclip = -IMAX, rm = besta;
+              for (int ch = 0; ch < 2; ch++)
+                { const int r = ch * 16 + hl, k = kh - r;  // ballot bit i of a half <-> r = ch*16 + i
+                  const bool act = wid && (r < width);
+                  int c = NEG, y = 0, hit = 0, ha = 0, hb = 0, ma = 0, mb = 0, na = 0, nb = 0;
+                  int cntA = 0, skipA = 0, cntB = 0, skipB = 0;
+                  uint64_t t = 0;
+                  if (act)
+                    { // old band = (kl, kh) exclusive: the two outer diagonals are new this wave
+                      const int vp = (k + 1 < kh) ? WF(F_V, cur, k + 1) : NEG;
+                      const int vc = (k > kl && k < kh) ? WF(F_V, cur, k) : NEG;
+                      const int vn = (k - 1 > kl) ? WF(F_V, cur, k - 1) : NEG;
+                      int src;
+                      if (vc < vn)                        // align.c:712-741 / 1367-1396
+                        { if (vn < vp) { c = vp + 1; src = k + 1; }
+                          else         { c = vn + 1; src = k - 1; }
+                        }
+                      else
+                        { if (vc < vp) { c = vp + 1; src = k + 1; }
+                          else         { c = vc + 2; src = k; }
+                        }
+                      t = ((uint64_t) (uint32_t) WF(F_TH, cur, src) << 32) | (uint32_t) WF(F_TL, cur, src);
+                      ha = WF(F_HA, cur, src); ma = WF(F_MA, cur, src);
+                      if (DOB) { hb = WF(F_HB, cur, src); mb = WF(F_MB, cur, src); }
+                      na = WNA(k); nb = WNB(k);
+                      t = (t << 1) | 1ull;
+                      const int y0 = (c - k) >> 1;
+                      y = slide2(aw, bw, asd, bsd, dir, aend, bend, k, y0, hit);
+                      const int run = y - y0;
+                      t = (run >= 64) ? 0ull : (t << run);
+                      c = (y << 1) + k;
+                      crossings(y + k, na, ma, TS, cntA, skipA);
+                      if (DOB) crossings(y, nb, mb, TS, cntB, skipB);
+                    }
+                  { int remA = cntA - skipA, remB = cntB - skipB;
+                    int nxA = na + TS * skipA, nxB = nb + TS * skipB;
+                    unsigned pa = __ballot_sync(FULL, remA > 0), pb = __ballot_sync(FULL, remB > 0);
+                    while (pa | pb)
+                      { const unsigned a16 = MY16(pa), b16 = MY16(pb), lt = (1u << hl) - 1;
+                        const int na_ = __popc(a16), tot = na_ + __popc(b16);
+                        if (avail + tot > cellcap)
+                          { if (tot) status = DERR_CELLS;
+                            remA = remB = 0;
+                          }
+                        else
+                          { if (remA > 0)
+                              { const int ix = avail + __popc(a16 & lt);
+                                cells[ix] = LPebble{ ha, dir * k, dif, dir * nxA };
+                                ha = ix; ma = nxA; nxA += TS; remA -= 1;
+                              }
+                            if (remB > 0)
+                              { const int ix = avail + na_ + __popc(b16 & lt);
+                                cells[ix] = LPebble{ hb, dir * k, dif, dir * nxB };
+                                hb = ix; mb = nxB; nxB += TS; remB -= 1;
+                              }
+                            avail += tot;
+                          }
+                        pa = __ballot_sync(FULL, remA > 0); pb = __ballot_sync(FULL, remB > 0);
+                      }
+                  }
+                  if (act)
+                    { WNA(k) = na + TS * cntA; WF(F_V, nxt, k) = c;
+                      WF(F_TL, nxt, k) = (int) (uint32_t) t; WF(F_TH, nxt, k) = (int) (uint32_t) (t >> 32);
+                      WF(F_HA, nxt, k) = ha; WF(F_MA, nxt, k) = ma;
+                      if (DOB) { WNB(k) = nb + TS * cntB; WF(F_HB, nxt, k) = hb; WF(F_MB, nxt, k) = mb; }
+                    }
+                  // record breakers, the running maximum carries over from the first chunk
+                  { const unsigned cb = __ballot_sync(FULL, c > besta);
+                    unsigned rest = MY16(cb), brk = 0;
+                    while (__any_sync(FULL, rest != 0))
+                      { const int i = __ffs(rest) - 1;
+                        const int v = SHF(c, i);
+                        if (rest != 0 && v > rm) { rm = v; brk |= 1u << i; }
+                        rest &= rest - 1;
+                      }
+                    const bool isb = act && ((brk >> hl) & 1u);
+                    const bool good = isb && (__popcll(t & HIST61) <= mgood);
+                    const bool trim = good && trim_ok(t, A.spec, sc0);
+                    const unsigned gs = MY16(__ballot_sync(FULL, good)), ts = MY16(__ballot_sync(FULL, trim));
+                    const int cg = SHF(c, 31 - __clz(gs));
+                    if (brk)
+                      { blane = 31 - __clz(brk);
+                        if (hl == blane) bY = y;
+                        if (gs) lasta = cg;
+                        if (ts)
+                          { tlane = 31 - __clz(ts);
+                            trimd = dif;
+                            if (hl == tlane) { tC = c; tY = y; tHA = ha; tHB = hb; }
+                          }
+                      }
+                  }
+                  { const unsigned as_ = MY16(__ballot_sync(FULL, act && hit == 2));
+                    const unsigned bs_ = MY16(__ballot_sync(FULL, act && hit == 1));
+                    if (as_ | bs_) more = 0;
+                    if (as_) aclip = kh - (ch * 16 + 31 - __clz(as_));        // last writer in scan order
+                    if (bs_ && bclip == -IMAX) bclip = kh - (ch * 16 + __ffs(bs_) - 1);   // first in scan order
+                  }
+                }
+              if (wid) besta = rm;
+              __syncwarp();
+              if (wid) cur = nxt;
+              const int ybw = SHF(bY, blane), moremw = C.morem;
+              __syncwarp();
+              if (wid && more == 0)                       // align.c:848-875 / 1502-1529
+                { const int yb = ybw, xb = besta - yb;
+                  if (yb >= C.blo && yb < bend && xb >= C.alo && xb < aend)
                     more = 1;
-                  int morem = morem0;
+                  int morem = moremw;
                   if (hgh >= aclip)
                     { hgh = aclip - 1;
+                      const uint64_t ta = ((uint64_t) (uint32_t) WF(F_TH, cur, aclip) << 32) | (uint32_t) WF(F_TL, cur, aclip);
+                      const int am = hist_m(ta);
                       if (morem <= am)
                         { morem = am;
+                          const int av = WF(F_V, cur, aclip);
                           if (lead)
                             { C.morem = am; C.morea = av; C.morey = (av - aclip) / 2; C.mored = dif;
-                              C.moreha = aha; C.morehb = ahb;
+                              C.moreha = WF(F_HA, cur, aclip); C.morehb = WF(F_HB, cur, aclip);
                             }
                         }
                     }
                   if (low <= bclip)
                     { low = bclip + 1;
+                      const uint64_t tb2 = ((uint64_t) (uint32_t) WF(F_TH, cur, bclip) << 32) | (uint32_t) WF(F_TL, cur, bclip);
+                      const int bm = hist_m(tb2);
                       if (morem <= bm)
-                        { if (lead)
+                        { const int bv = WF(F_V, cur, bclip);
+                          if (lead)
                             { C.morem = bm; C.morea = bv; C.morey = (bv - bclip) / 2; C.mored = dif;
-                              C.moreha = bha; C.morehb = bhb;
+                              C.moreha = WF(F_HA, cur, bclip); C.morehb = WF(F_HB, cur, bclip);
                             }
                         }
                     }
                 }
               __syncwarp();
-            }
-
-          // trim the band to within WAVE_LAG of the best point (align.c:877-885 / 1531-1539)
-          { const unsigned g = __ballot_sync(FULL, act && k >= low && k <= hgh && rV >= besta - WAVE_LAG);
-            const unsigned gsn = SCAN16(MY16(g));
-            if (nar)
-              { if (gsn)
-                  { hgh = kh - (__ffs(gsn) - 1);
-                    low = kh - (31 - __clz(gsn));
-                  }
-                else
-                  hgh = low - 1;
-                nwaves += 1;
-                ncells += (unsigned) (hgh - low + 1);
-              }
-          }
-        }
-
-      // =================================== wide wave: 17..32 diagonals, state in the window
-      const bool wid = go && wide;
-      if (__any_sync(FULL, wid))
-        { if (wid) { low -= 1; hgh += 1; dif += 1; }
-          const int kh = hgh, kl = low;
-          const int width = wid ? hgh - low + 1 : 0;
-          const int nxt = cur ^ 1;
-          if (wid && lead)
-            { WNA(kl) = WNA(kl + 1); WNA(kh) = WNA(kh - 1);
-              if (DOB) { WNB(kl) = WNB(kl + 1); WNB(kh) = WNB(kh - 1); }
-            }
-          __syncwarp();
-          int aclip = IMAX, bclip = -IMAX, rm = besta;
-          for (int ch = 0; ch < 2; ch++)
-            { const int r = ch * 16 + hl, k = kh - r;
-              const bool act = wid && (r < width);
-              const int s = 0;                            // ballot bit i of a half <-> r = ch*16 + i
-              int c = NEG, y = 0, hit = 0, ha = 0, hb = 0, ma = 0, mb = 0, na = 0, nb = 0;
-              int cntA = 0, skipA = 0, cntB = 0, skipB = 0;
-              uint64_t t = 0;
-              if (act)
-                { // old band = (kl, kh) exclusive: the two outer diagonals are new this wave
-                  const int vp = (k + 1 < kh) ? WF(F_V, cur, k + 1) : NEG;
-                  const int vc = (k > kl && k < kh) ? WF(F_V, cur, k) : NEG;
-                  const int vn = (k - 1 > kl) ? WF(F_V, cur, k - 1) : NEG;
-                  int src;
-                  if (vc < vn)                            // align.c:712-741 / 1367-1396
-                    { if (vn < vp) { c = vp + 1; src = k + 1; }
-                      else         { c = vn + 1; src = k - 1; }
-                    }
-                  else
-                    { if (vc < vp) { c = vp + 1; src = k + 1; }
-                      else         { c = vc + 2; src = k; }
-                    }
-                  t = ((uint64_t) (uint32_t) WF(F_TH, cur, src) << 32) | (uint32_t) WF(F_TL, cur, src);
-                  ha = WF(F_HA, cur, src); ma = WF(F_MA, cur, src);
-                  if (DOB) { hb = WF(F_HB, cur, src); mb = WF(F_MB, cur, src); }
-                  na = WNA(k); nb = WNB(k);
-                  t = (t << 1) | 1ull;
-                  const int y0 = (c - k) >> 1;
-                  y = slide2(aw, bw, asd, bsd, dir, aend, bend, k, y0, hit);
-                  const int run = y - y0;
-                  t = (run >= 64) ? 0ull : (t << run);
-                  c = (y << 1) + k;
-                  crossings(y + k, na, ma, TS, cntA, skipA);
-                  if (DOB) crossings(y, nb, mb, TS, cntB, skipB);
+              // trim the band (align.c:877-885 / 1531-1539)
+              { const int n = besta - WAVE_LAG;
+                unsigned g0, g1;
+                { const int k = kh - hl;
+                  g0 = MY16(__ballot_sync(FULL, wid && hl < width && k >= low && k <= hgh && WF(F_V, cur, k) >= n));
                 }
-              { int remA = cntA - skipA, remB = cntB - skipB;
-                int nxA = na + TS * skipA, nxB = nb + TS * skipB;
-                unsigned pa = __ballot_sync(FULL, remA > 0), pb = __ballot_sync(FULL, remB > 0);
-                while (pa | pb)
-                  { const unsigned a16 = MY16(pa), b16 = MY16(pb), lt = (1u << hl) - 1;
-                    const int na_ = __popc(a16), tot = na_ + __popc(b16);
-                    if (avail + tot > cellcap)
-                      { if (tot) status = DERR_CELLS;
-                        remA = remB = 0;
+                { const int k = kh - 16 - hl;
+                  g1 = MY16(__ballot_sync(FULL, wid && 16 + hl < width && k >= low && k <= hgh && WF(F_V, cur, k) >= n));
+                }
+                const unsigned g = g0 | (g1 << 16);
+                if (wid)
+                  { if (g)
+                      { hgh = kh - (__ffs(g) - 1);
+                        low = kh - (31 - __clz(g));
                       }
                     else
-                      { if (remA > 0)
-                          { const int ix = avail + __popc(a16 & lt);
-                            cells[ix] = LPebble{ ha, dir * k, dif, dir * nxA };
-                            ha = ix; ma = nxA; nxA += TS; remA -= 1;
-                          }
-                        if (remB > 0)
-                          { const int ix = avail + na_ + __popc(b16 & lt);
-                            cells[ix] = LPebble{ hb, dir * k, dif, dir * nxB };
-                            hb = ix; mb = nxB; nxB += TS; remB -= 1;
-                          }
-                        avail += tot;
-                      }
-                    pa = __ballot_sync(FULL, remA > 0); pb = __ballot_sync(FULL, remB > 0);
+                      hgh = low - 1;
+                    ncells += (unsigned) (hgh - low + 1);
                   }
               }
-              if (act)
-                { WNA(k) = na + TS * cntA; WF(F_V, nxt, k) = c;
-                  WF(F_TL, nxt, k) = (int) (uint32_t) t; WF(F_TH, nxt, k) = (int) (uint32_t) (t >> 32);
-                  WF(F_HA, nxt, k) = ha; WF(F_MA, nxt, k) = ma;
-                  if (DOB) { WNB(k) = nb + TS * cntB; WF(F_HB, nxt, k) = hb; WF(F_MB, nxt, k) = mb; }
-                }
-              // record breakers, the running maximum carries over from the first chunk
-              { const unsigned cb = __ballot_sync(FULL, c > besta);
-                unsigned rest = MY16(cb), brk = 0;
-                while (__any_sync(FULL, rest != 0))
-                  { const int i = __ffs(rest) - 1;
-                    const int v = SHF(c, i);
-                    if (rest != 0 && v > rm) { rm = v; brk |= 1u << i; }
-                    rest &= rest - 1;
-                  }
-                const bool isb = act && ((brk >> hl) & 1u);
-                const bool good = isb && (__popcll(t & HIST61) <= mgood);
-                const bool trim = good && trim_ok(t, A.spec);
-                const unsigned gs = MY16(__ballot_sync(FULL, good)), ts = MY16(__ballot_sync(FULL, trim));
-                const int cg = SHF(c, 31 - __clz(gs));
-                if (brk)
-                  { blane = 31 - __clz(brk);
-                    if (hl == blane) bY = y;
-                    if (gs) lasta = cg;
-                    if (ts)
-                      { tlane = 31 - __clz(ts);
-                        trimd = dif;
-                        if (hl == tlane) { tC = c; tY = y; tHA = ha; tHB = hb; }
-                      }
-                  }
-              }
-              { const unsigned as_ = MY16(__ballot_sync(FULL, act && hit == 2));
-                const unsigned bs_ = MY16(__ballot_sync(FULL, act && hit == 1));
-                if (as_ | bs_) more = 0;
-                if (as_) aclip = kh - (ch * 16 + 31 - __clz(as_));        // last writer in scan order
-                if (bs_ && bclip == -IMAX) bclip = kh - (ch * 16 + __ffs(bs_) - 1);   // first in scan order
-              }
-              (void) s;
             }
-          if (wid) besta = rm;
+
+          nar = go && !wide;
+          if (!__any_sync(FULL, nar))
+            continue;
           __syncwarp();
-          if (wid) cur = nxt;
-          const int ybw = SHF(bY, blane), moremw = C.morem;
+        }
+
+      // =================================== narrow wave: one diagonal per lane, state in registers
+      DBG_CP(0);
+      if (nar) { low -= 1; hgh += 1; dif += 1; }
+      const int kh = hgh;                                 // lane mapping of this wave
+      const int s = (-kh) & 15, r = (hl - s) & 15, k = kh - r;
+      const int width = hgh - low + 1;
+      const bool act = nar && (r < width);
+      const bool old = act && r > 0 && r < width - 1;     // the diagonal existed before this wave
+      const int vold = old ? rV : NEG;
+      const int vp = SHF(vold, hl - 1), vn = SHF(vold, hl + 1);     // diagonals k+1, k-1
+      int c, srcl;
+      if (vold < vn)                                      // align.c:712-741 / 1367-1396
+        { if (vn < vp) { c = vp + 1; srcl = hl - 1; }
+          else         { c = vn + 1; srcl = hl + 1; }
+        }
+      else
+        { if (vold < vp) { c = vp + 1; srcl = hl - 1; }
+          else           { c = vold + 2; srcl = hl; }
+        }
+      uint64_t t;
+      { const unsigned tl = SHF((unsigned) rT, srcl), th = SHF((unsigned) (rT >> 32), srcl);
+        t = ((uint64_t) th << 32) | tl;
+      }
+      int ha = SHF(rHA, srcl), ma = SHF(rMA, srcl), hb = 0, mb = 0;
+      // a new outer diagonal takes NA/NB of its inner neighbour (align.c:678-690), which is its source
+      { const int nas = SHF(rNA, srcl);
+        if (act && !old) rNA = nas;
+      }
+      if (DOB)
+        { hb = SHF(rHB, srcl); mb = SHF(rMB, srcl);
+          const int nbs = SHF(rNB, srcl);
+          if (act && !old) rNB = nbs;
+        }
+      int y = 0, hit = 0, remA = 0, remB = 0, nxA = 0, nxB = 0;
+      DBG_CP(1);
+      if (act)
+        { t = (t << 1) | 1ull;                             // the difference
+          const int y0 = (c - k) >> 1;
+          y = slide2(aw, bw, asd, bsd, dir, aend, bend, k, y0, hit);
+          const int run = y - y0;
+          t = (run >= 64) ? 0ull : (t << run);             // matches
+          c = (y << 1) + k;
+          int cnt, skip;
+          crossings(y + k, rNA, ma, TS, cnt, skip);        // align.c:771-793 / 1426-1448
+          remA = cnt - skip; nxA = rNA + TS * skip; rNA += TS * cnt;
+          if (DOB)
+            { crossings(y, rNB, mb, TS, cnt, skip);        // align.c:795-817 / 1449-1471
+              remB = cnt - skip; nxB = rNB + TS * skip; rNB += TS * cnt;
+            }
+        }
+      else
+        c = NEG;
+
+      // Pebble cells (numbered by ballot rank, one A and one B cell per lane and round); sequence ends
+      DBG_CP(2);
+      bool anyhit = false;
+      if (__any_sync(FULL, (remA > 0) || (remB > 0) || (hit != 0)))
+        { DBG_EV(16);
+          unsigned pa = __ballot_sync(FULL, remA > 0), pb = __ballot_sync(FULL, remB > 0);
+          while (pa | pb)
+            { const unsigned a16 = MY16(pa), b16 = MY16(pb), lt = (1u << hl) - 1;
+              const int na_ = __popc(a16), tot = na_ + __popc(b16);
+              if (avail + tot > cellcap)
+                { if (tot) status = DERR_CELLS;
+                  remA = remB = 0;
+                }
+              else
+                { if (remA > 0)
+                    { const int ix = avail + __popc(a16 & lt);
+                      cells[ix] = LPebble{ ha, dir * k, dif, dir * nxA };
+                      ha = ix; ma = nxA; nxA += TS; remA -= 1;
+                    }
+                  if (remB > 0)
+                    { const int ix = avail + na_ + __popc(b16 & lt);
+                      cells[ix] = LPebble{ hb, dir * k, dif, dir * nxB };
+                      hb = ix; mb = nxB; nxB += TS; remB -= 1;
+                    }
+                  avail += tot;
+                }
+              pa = __ballot_sync(FULL, remA > 0); pb = __ballot_sync(FULL, remB > 0);
+            }
+          anyhit = __any_sync(FULL, hit != 0);
+        }
+      DBG_CP(3);
+      if (act)
+        { rV = c; rT = t; rHA = ha; rMA = ma;
+          if (DOB) { rHB = hb; rMB = mb; }
+        }
+
+      // record breakers in scan order (align.c:819-833 / 1473-1487): a point breaks the record when it
+      // lies beyond besta and beyond every point before it in the scan -- an exclusive prefix maximum
+      // over the circular lane order
+      { int pm = c;                                       // NEG on lanes outside the band
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1)
+          { const int q = SHF(pm, hl - o);
+            if (r >= o) pm = max(pm, q);
+          }
+        int before = SHF(pm, hl - 1);
+        before = (r == 0) ? besta : max(before, besta);
+        const bool isb = act && (c > before);
+        const bool good = isb && (__popcll(t & HIST61) <= mgood);
+        const bool trim = good && trim_ok(t, A.spec, sc0);
+        const unsigned rb = ROT16(__ballot_sync(FULL, isb)), rg = ROT16(__ballot_sync(FULL, good));
+        const unsigned rt = ROT16(__ballot_sync(FULL, trim));
+        const int bl = (s + 15 - __clz(rb)) & 15, gl = s + 15 - __clz(rg);
+        const int cb = SHF(c, bl), cg = SHF(c, gl);
+        if (rb)
+          { besta = cb; blane = bl;
+            if (hl == bl) bY = y;
+          }
+        if (rg) lasta = cg;
+        if (rt)
+          { tlane = (s + 15 - __clz(rt)) & 15;
+            trimd = dif;
+            if (hl == tlane) { tC = c; tY = y; tHA = ha; tHB = hb; }
+          }
+      }
+
+      // sequence ends (align.c:752-763,848-875 / 1407-1418,1502-1529)
+      DBG_CP(4);
+      if (anyhit)
+        { const unsigned as_ = ROT16(__ballot_sync(FULL, act && hit == 2)), bs_ = ROT16(__ballot_sync(FULL, act && hit == 1));
+          int aclip = IMAX, bclip = -IMAX;
+          if (as_ | bs_) more = 0;
+          if (as_) aclip = kh - (15 - __clz(as_));        // last writer in scan order
+          if (bs_) bclip = kh - (__ffs(bs_) - 1);         // extreme k towards the scan start
+          const bool clip = nar && (more == 0);
+          const int yb = SHF(bY, blane);
+          const int la = (-aclip) & 15, lb = (-bclip) & 15;
+          const int mloc = hist_m(rT), morem0 = C.morem, alo = C.alo, blo = C.blo;
           __syncwarp();
-          if (wid && more == 0)                           // align.c:848-875 / 1502-1529
-            { const int yb = ybw, xb = besta - yb;
-              if (yb >= C.blo && yb < bend && xb >= C.alo && xb < aend)
+          const int am = SHF(mloc, la), av = SHF(rV, la), aha = SHF(rHA, la), ahb = SHF(rHB, la);
+          const int bm = SHF(mloc, lb), bv = SHF(rV, lb), bha = SHF(rHA, lb), bhb = SHF(rHB, lb);
+          if (clip)
+            { const int xb = besta - yb;
+              if (yb >= blo && yb < bend && xb >= alo && xb < aend)
                 more = 1;
-              int morem = moremw;
+              int morem = morem0;
               if (hgh >= aclip)
                 { hgh = aclip - 1;
-                  const uint64_t ta = ((uint64_t) (uint32_t) WF(F_TH, cur, aclip) << 32) | (uint32_t) WF(F_TL, cur, aclip);
-                  const int am = hist_m(ta);
                   if (morem <= am)
                     { morem = am;
-                      const int av = WF(F_V, cur, aclip);
                       if (lead)
                         { C.morem = am; C.morea = av; C.morey = (av - aclip) / 2; C.mored = dif;
-                          C.moreha = WF(F_HA, cur, aclip); C.morehb = WF(F_HB, cur, aclip);
+                          C.moreha = aha; C.morehb = ahb;
                         }
                     }
                 }
               if (low <= bclip)
                 { low = bclip + 1;
-                  const uint64_t tb2 = ((uint64_t) (uint32_t) WF(F_TH, cur, bclip) << 32) | (uint32_t) WF(F_TL, cur, bclip);
-                  const int bm = hist_m(tb2);
                   if (morem <= bm)
-                    { const int bv = WF(F_V, cur, bclip);
-                      if (lead)
+                    { if (lead)
                         { C.morem = bm; C.morea = bv; C.morey = (bv - bclip) / 2; C.mored = dif;
-                          C.moreha = WF(F_HA, cur, bclip); C.morehb = WF(F_HB, cur, bclip);
+                          C.moreha = bha; C.morehb = bhb;
                         }
                     }
                 }
             }
           __syncwarp();
-          // trim the band (align.c:877-885 / 1531-1539)
-          { const int n = besta - WAVE_LAG;
-            unsigned g0, g1;
-            { const int k = kh - hl;
-              g0 = MY16(__ballot_sync(FULL, wid && hl < width && k >= low && k <= hgh && WF(F_V, cur, k) >= n));
-            }
-            { const int k = kh - 16 - hl;
-              g1 = MY16(__ballot_sync(FULL, wid && 16 + hl < width && k >= low && k <= hgh && WF(F_V, cur, k) >= n));
-            }
-            const unsigned g = g0 | (g1 << 16);
-            if (wid)
-              { if (g)
-                  { hgh = kh - (__ffs(g) - 1);
-                    low = kh - (31 - __clz(g));
-                  }
-                else
-                  hgh = low - 1;
-                nwaves += 1;
-                ncells += (unsigned) (hgh - low + 1);
-              }
-          }
         }
+
+      // trim the band to within WAVE_LAG of the best point (align.c:877-885 / 1531-1539)
+      DBG_CP(5);
+      { const unsigned g = ROT16(__ballot_sync(FULL, act && k >= low && k <= hgh && rV >= besta - WAVE_LAG));
+        if (nar)
+          { if (g)
+              { hgh = kh - (__ffs(g) - 1);
+                low = kh - (15 - __clz(g));
+              }
+            else
+              hgh = low - 1;
+            ncells += (unsigned) (hgh - low + 1);
+          }
+      }
     }
 
   if (lead)
@@ -850,8 +904,9 @@ k_align_duo(const __grid_constant__ AlignArgs A)
 #undef WNA
 #undef WNB
 #undef SHF
+#undef DUP16
 #undef MY16
-#undef SCAN16
+#undef ROT16
 }
 
 size_t duo_smem_bytes()
@@ -877,6 +932,20 @@ void launch_align_duo(const AlignArgs &A, int njobs, cudaStream_t stream)
   if (nblocks > cap) nblocks = cap;
   if (dob) LAUNCH(k_align_duo<true>, nblocks, DUO_WARPS * 32, smem, stream, A);
   else     LAUNCH(k_align_duo<false>, nblocks, DUO_WARPS * 32, smem, stream, A);
+#ifdef DUO_DEBUG_DIV
+  { unsigned long long h[64];
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(h, g_duo_dbg, sizeof(h));
+    fprintf(stderr, "[duo dbg] rounds converged %llu split %llu\n  became split after events:", h[0], h[1]);
+    for (int i = 0; i < 32; i++) if (h[8 + i]) fprintf(stderr, " %d:%llu", i, h[8 + i]);
+    fprintf(stderr, "\n  became converged after events:");
+    for (int i = 0; i < 16; i++) if (h[40 + i]) fprintf(stderr, " %d:%llu", i, h[40 + i]);
+    fprintf(stderr, "\n  split at checkpoints:");
+    for (int i = 0; i < 8; i++) fprintf(stderr, " %d:%llu", i, h[56 + i]);
+    fprintf(stderr, "\n");
+    memset(h, 0, sizeof(h)); cudaMemcpyToSymbol(g_duo_dbg, h, sizeof(h));
+  }
+#endif
 }
 
 }  // namespace damgpu
