@@ -115,8 +115,8 @@ __device__ __forceinline__ int hist_m(uint64_t t) { return PATH_LEN + 1 - __popc
 __device__ __forceinline__ bool trim_ok(uint64_t t, const AlignSpecD &sp, int sc0)
 { const uint32_t b = ~(uint32_t) t;
   const int lo15 = (int) (b & TRIM_MASK), hi15 = (int) ((b >> TRIM_LEN) & TRIM_MASK);
-  if (__ldg(sp.table + lo15) < 0) return false;
-  return (__ldg(sp.table + hi15) + 1000 * __popc(lo15) + sc0 >= 0);
+  const int t_lo = __ldg(sp.table + lo15), t_hi = __ldg(sp.table + hi15);   // both in flight at once
+  return (t_lo >= 0) && (t_hi + 1000 * __popc(lo15) + sc0 >= 0);
 }
 
 // how many trace coordinates n, n+TS, .. the point p has reached, and how many of those the
@@ -387,7 +387,6 @@ k_align_duo(const __grid_constant__ AlignArgs A)
 { extern __shared__ __align__(16) unsigned char dsm[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int half = lane >> 4, hl = lane & 15;
-  const unsigned hmask = 0xffffu << (half * 16);
   const unsigned dupsel = half ? 0x3232u : 0x1010u;       // PRMT selector: own ballot half, twice
   const bool lead = (hl == 0);
   DuoCtl &C = reinterpret_cast<DuoCtl *>(dsm)[wib * 2 + half];
