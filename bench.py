@@ -2,20 +2,26 @@
 """bench.py -- mapped read bases/sec of the B200 mapping core on BASELINE.json's metric config.
 
 Workload (config.workload): BASELINE config 2 -- synthetic 4.6 Mbp reference (2 contigs) and
-30x coverage of simulated 10 kbp reads at 15 % error (13 800 reads, ~138 Mbp), k=20, defaults.
+30x coverage of simulated 10 kbp reads at 15 % error (13 800 reads, ~140 Mbp), k=20, defaults.
 A step = the whole hot path for one reads block: Sort_Kmers(reads), then per reference block
 Sort_Kmers + Match_Filter for both orientations, then Reporter (chain extension, selection,
 records copied back).  N > 1 (torchrun, one rank per GPU): every rank maps its own reads
-block (weak scaling); the forward and complement reference indices are built on rank 0 and
-broadcast over NCCL, reads need no collective.
+block (weak scaling); reads need no collective.  The reference index (2 x 74 MB here) is built by
+every rank for itself by default: at this size the local build (0.3 ms) is cheaper than an NCCL
+broadcast with its length exchange (measured 0.7 ms per step in round 1); --index broadcast
+builds it on rank 0 and broadcasts it (the form for chromosome-scale references).
 
   value  inputs resident in HBM when the timed region starts (blocks already uploaded)
   e2e    through the reference-facing C ABI (the four map.h calls) with host buffers in pinned
-         memory: H2D of the blocks and D2H of the records are inside the timed region
+         memory: H2D of the blocks and D2H of the records are inside the timed region.  The reads
+         block is handed over as the .bps image (2 bits per base, damgpu_block.packed) -- the form
+         the DB holds on disk -- the reference blocks as Load_All_Reads leaves them.
+  whole_process  exec -> exit of the two command lines on the same DB files:
+         damapper_b200/damapper and oracle/_ref/damapper, LAsort/LAcat stubbed for both.
 
---impl reference times the unmodified reference damapper (oracle/_ref, built from
-/root/reference by oracle/Makefile) on the host cores, on a bounded sample of the same
-workload; the oracle directory is touched only there and in the cpu_baseline leg.
+--impl reference times the unmodified reference damapper (oracle/_ref, built from /root/reference
+by oracle/Makefile) on the host cores on the whole workload, whole process; the oracle directory
+is touched only there and in the cpu_baseline / whole_process legs.
 """
 from __future__ import annotations
 
@@ -46,6 +52,14 @@ def peaks():
             return float(json.load(f)["hbm_gbs"]), "measured"
     except Exception:
         return 6650.0, "fallback"
+
+
+def profile_json(name):
+    try:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 class ClockSampler(threading.Thread):
@@ -84,7 +98,7 @@ class ClockSampler(threading.Thread):
 
 
 def make_workload(seed: int, reads_scale: float = 1.0):
-    from damapper_b200 import synth, dazzdb
+    from damapper_b200 import synth
     contigs, rb, rl = synth.make_config("C2", scale=1.0, seed=7)     # the reference is shared
     if seed != 7 or reads_scale != 1.0:
         genome = np.concatenate(contigs)
@@ -96,20 +110,78 @@ def make_workload(seed: int, reads_scale: float = 1.0):
     return contigs, rb, rl, freq
 
 
-def pinned_block(api, loaded, torch):
-    """HostBlock whose base array lives in pinned host memory."""
-    bases, boff, rlen = loaded
-    t = torch.empty(bases.size, dtype=torch.uint8, pin_memory=True)
-    t.numpy()[:] = bases
-    hb = api.HostBlock(t.numpy(), boff, rlen)
-    hb._pin = t
-    return hb
+def host_threads():
+    cores = os.cpu_count() or 1
+    threads = 1
+    while 2 * threads <= cores:
+        threads *= 2                                 # the reference rounds -T down to 2^n (map.c:142-147)
+    return threads
+
+
+def config_of(nreads, bases, n_kmers, index):
+    """The same keys from both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "reads_per_gpu": int(nreads), "read_bases_per_gpu": int(bases), "kmer": 20,
+            "l2": "inputs larger than L2 (126 MB): the reads block is %.0f MB at one byte per base (35 MB packed), its "
+                  "k-mer list %.1f GB; no flush between steps" % (bases / 1e6, 16.0 * n_kmers / 1e9),
+            "index": index}
+
+
+# ------------------------------------------------------------------ the two command lines
+
+def run_cli(wd, exe, threads, env_extra=None):
+    """exec -> exit of a damapper command line in wd (stubs for LAsort/LAcat/LAmerge on PATH)."""
+    from oracle import run_ref                       # test infrastructure: CPU legs only
+    r = run_ref.run_damapper(wd, "ref.dam", "reads.db", flags=("-M64",), threads=threads, exe=exe,
+                             env_extra=env_extra)
+    return r
+
+
+def whole_process(contigs, rb, rl, device, runs=3):
+    """whole process, both command lines, same DB files, same stubs.  Returns
+    (dict for the JSON line, cpu_baseline dict)."""
+    from damapper_b200 import dazzdb
+    from oracle import run_ref
+    if not run_ref.have_ref():
+        return None, None
+    threads = host_threads()
+    bases = int(rl.sum())
+    wd = tempfile.mkdtemp(prefix="bench_wp_")
+    gpu_exe = os.path.join(ROOT, "damapper_b200", "damapper")
+    timed = os.path.join(run_ref.REF_DIR, "damapper_timed")
+    ref_w, gpu_w, core = [], [], None
+    try:
+        dazzdb.write_db(os.path.join(wd, "ref.dam"), contigs, is_dam=True)
+        dazzdb.write_db(os.path.join(wd, "reads.db"), (rb, rl))
+        for it in range(runs):
+            ref_w.append(run_cli(wd, None, threads)["wall_s"])
+            if os.access(gpu_exe, os.X_OK):
+                gpu_w.append(run_cli(wd, gpu_exe, threads, {"DAMGPU_DEVICE": str(device)})["wall_s"])
+        if os.access(timed, os.X_OK):
+            core = run_cli(wd, timed, threads)["core_s"]
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+    sample = ("reference damapper -T%d -M64 on the whole workload (%d reads, %d bases) vs the full 4.6 Mbp reference, "
+              "whole process (exec -> exit, DB load and .las writes, LAsort/LAcat stubbed), median of %d runs"
+              % (threads, len(rl), bases, runs))
+    wp = {"boundary": "exec -> exit of the command line on the same DB files, LAsort/LAcat/LAmerge stubbed for both",
+          "reference": {"wall_s_median": float(np.median(ref_w)), "wall_s_min": float(min(ref_w)), "runs_s": ref_w,
+                        "threads": threads, "value": bases / float(np.median(ref_w)), "unit": UNIT,
+                        "core_only_s": core,
+                        "core_only_note": "sum of the Sort_Kmers/Match_Filter/Reporter calls (damapper.c:833-875), "
+                                          "clocked by ld --wrap around the unmodified sources (oracle/ref_timing.c)"}}
+    if gpu_w:
+        wp["gpu"] = {"wall_s_median": float(np.median(gpu_w)), "wall_s_min": float(min(gpu_w)), "runs_s": gpu_w,
+                     "value": bases / float(np.median(gpu_w)), "unit": UNIT,
+                     "note": "a fresh process pays cuInit + context creation (0.6-3 s on these boxes, DESIGN section 7) "
+                             "before ~60 ms of work; e2e is the same path in a warm process"}
+    cpu = {"value": bases / float(np.median(ref_w)), "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample}
+    return wp, cpu
 
 
 # ---------------------------------------------------------------------------- reference arm
 
 def run_reference(args):
-    """Unmodified reference damapper -T<host cores> on a bounded sample of the workload."""
+    """Unmodified reference damapper -T<host cores> on the whole workload, whole process."""
     from damapper_b200 import dazzdb
     from oracle import run_ref                       # test infrastructure, CPU arm only
     rank = int(os.environ.get("RANK", "0"))
@@ -118,71 +190,60 @@ def run_reference(args):
     if not run_ref.have_ref():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/damapper is not built"}))
         return
-    cores = os.cpu_count() or 1
-    threads = 1
-    while 2 * threads <= cores:
-        threads *= 2                                 # the reference rounds -T down to 2^n (map.c:142-147)
+    threads = host_threads()
     contigs, rb, rl, freq = make_workload(seed=7)
-    sample_reads = len(rl)                           # the whole workload: ~1.2 s per run on 16 threads (~19 CPU-seconds)
-    off = np.concatenate([[0], np.cumsum(rl)])
-    rb_s, rl_s = rb[:off[sample_reads]], rl[:sample_reads]
-    bases = int(rl_s.sum())
+    bases = int(rl.sum())
+    n_kmers = int((rl - 19).sum())
     wd = tempfile.mkdtemp(prefix="bench_ref_")
-    times = []
+    times, core = [], None
     try:
         dazzdb.write_db(os.path.join(wd, "ref.dam"), contigs, is_dam=True)
-        dazzdb.write_db(os.path.join(wd, "reads.db"), (rb_s, rl_s))
+        dazzdb.write_db(os.path.join(wd, "reads.db"), (rb, rl))
         for it in range(args.warmup + args.steps):
-            r = run_ref.run_damapper(wd, "ref.dam", "reads.db", flags=("-M64",), threads=threads)
+            r = run_cli(wd, None, threads)
             if it >= args.warmup:
                 times.append(r["wall_s"])
+        timed = os.path.join(run_ref.REF_DIR, "damapper_timed")
+        if os.access(timed, os.X_OK):
+            core = run_cli(wd, timed, threads)["core_s"]
     finally:
         shutil.rmtree(wd, ignore_errors=True)
     t = float(np.mean(times))
     val = bases / t
     sample = ("the whole workload (%d reads, %d bases) against the full 4.6 Mbp reference, damapper -T%d -M64, "
-              "whole process wall clock incl. DB load and .las writes, LAsort/LAcat stubbed" % (sample_reads, bases, threads))
+              "whole process wall clock incl. DB load and .las writes, LAsort/LAcat stubbed" % (len(rl), bases, threads))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "config": config_of(len(rl), bases, n_kmers, "built locally"),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "whole_process": {"reference": {"wall_s_mean": t, "threads": threads, "core_only_s": core}},
     }))
 
 
-def cpu_baseline():
-    """Reference damapper on the host cores, bounded sample (rank 0, N=1 only)."""
-    from damapper_b200 import dazzdb
-    from oracle import run_ref
-    if not run_ref.have_ref():
-        return None
-    cores = os.cpu_count() or 1
-    threads = 1
-    while 2 * threads <= cores:
-        threads *= 2
-    contigs, rb, rl, freq = make_workload(seed=7)
-    sample_reads = len(rl)                           # the whole workload (~19 CPU-seconds per run)
-    off = np.concatenate([[0], np.cumsum(rl)])
-    rb_s, rl_s = rb[:off[sample_reads]], rl[:sample_reads]
-    wd = tempfile.mkdtemp(prefix="bench_cpu_")
-    try:
-        dazzdb.write_db(os.path.join(wd, "ref.dam"), contigs, is_dam=True)
-        dazzdb.write_db(os.path.join(wd, "reads.db"), (rb_s, rl_s))
-        best = None
-        for _ in range(2):
-            r = run_ref.run_damapper(wd, "ref.dam", "reads.db", flags=("-M64",), threads=threads)
-            best = r["wall_s"] if best is None else min(best, r["wall_s"])
-    finally:
-        shutil.rmtree(wd, ignore_errors=True)
-    bases = int(rl_s.sum())
-    return {"value": bases / best, "unit": UNIT, "cores": threads, "kind": "reference",
-            "sample": "reference damapper -T%d -M64 on the whole workload (%d reads, %d bases) vs the full 4.6 Mbp "
-                      "reference, best of 2, whole process" % (threads, sample_reads, bases)}
-
-
 # ---------------------------------------------------------------------------------- GPU arm
+
+def pinned_array(torch, a):
+    t = torch.empty(a.size, dtype=torch.uint8, pin_memory=True)
+    t.numpy()[:] = a.reshape(-1).view(np.uint8)
+    return t
+
+
+def pinned_block(api, loaded, torch, packed=False):
+    """HostBlock whose base array (and .bps image) live in pinned host memory."""
+    bases, boff, rlen = loaded
+    t = pinned_array(torch, bases)
+    hb = api.HostBlock(t.numpy(), boff, rlen)
+    hb._pin = [t]
+    if packed:
+        pk, poff = api.pack_bps(hb)
+        tp = pinned_array(torch, pk)
+        hb.attach_packed(tp.numpy(), poff)
+        hb._pin.append(tp)
+    return hb
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -190,6 +251,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="damgpu")
+    ap.add_argument("--index", default="local", choices=["local", "broadcast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -203,7 +265,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from damapper_b200 import api, dazzdb, shard
+    from damapper_b200 import api, dazzdb
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -215,13 +277,15 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = api.init(local)
     args.warmup = max(args.warmup, 3)
+    bcast = (world > 1 and args.index == "broadcast")
 
     # every rank maps its own reads block (different seed) against the same reference
     contigs, rb, rl, freq = make_workload(seed=7 + 100 * rank)
     rd = dazzdb.load_block((rb, rl))
     rf = dazzdb.load_block(contigs)
     rc = dazzdb.load_block(dazzdb.revcomp_contigs(contigs))
-    hr, hg, hc = pinned_block(api, rd, torch), pinned_block(api, rf, torch), pinned_block(api, rc, torch)
+    hr = pinned_block(api, rd, torch, packed=True)
+    hg, hc = pinned_block(api, rf, torch), pinned_block(api, rc, torch)
     bases = int(rl.sum())
     api.set_filter_params(20, 0, 4)
     api.set_options(mem_limit=64 << 30)
@@ -233,19 +297,25 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    nref = [0]
+
     def ref_index(dref):
-        """Reference index of the block's current orientation: built on rank 0, broadcast."""
-        if world == 1:
+        """Reference index of the block's current orientation."""
+        if not bcast:
             return api.Index(dref)
         idx, payload = None, None
         if rank == 0:
             idx = api.Index(dref)
+            nref[0] = len(idx)
             payload = torch.empty((len(idx) + 2) * 16, dtype=torch.uint8, device="cuda")
             L.damgpu_index_export(idx.h, payload.data_ptr())
-        buf, ln = shard.broadcast_index(dist, torch, payload, "cuda", src=0)
+        # every rank knows the length from the block itself (k-mers = sum(rlen - k + 1), map.c:676): no
+        # length exchange, no host synchronisation before the payload
+        ln = int((rf[2].astype(np.int64) - 19).clip(min=0).sum())
+        buf = payload if rank == 0 else torch.empty((ln + 2) * 16, dtype=torch.uint8, device="cuda")
+        dist.broadcast(buf, 0)
         if rank == 0:
             return idx
-        torch.cuda.synchronize()
         return api.Index(handle=L.damgpu_index_import(buf.data_ptr(), ln))
 
     stats = {}
@@ -291,6 +361,8 @@ def main():
     L.damgpu_time_kernels(1)
     for _ in range(args.warmup):
         nrec, nbytes = step_resident(dr, dg)
+    rtot = (C.c_double * 4)()
+    L.damgpu_radix_totals(rtot, 1)                       # reset: the timed steps only
     sampler = ClockSampler(local)
     sync_all()
     sampler.start()
@@ -298,10 +370,10 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     t0 = time.perf_counter()
-    sort_ms, sort_n, ext_ms, aln_ms, join_ms, flt, rsort = [], 0, [], [], [], [], []
+    sort_ms, sort_n, ext_ms, aln_ms, join_ms, flt = [], 0, [], [], [], []
     for _ in range(args.steps):
         nrec, nbytes = step_resident(dr, dg)
-        flt.append(stats["filter"]); rsort.append(stats["ref_sort"])
+        flt.append(stats["filter"])
         aln_ms.append(stats["report"]["align_ms"])
         join_ms.append(stats["join_fwd"]["lut_ms"] + stats["join_fwd"]["match_ms"] +
                        stats["join_rc"]["lut_ms"] + stats["join_rc"]["match_ms"])
@@ -309,6 +381,8 @@ def main():
     sync_all()
     t1 = time.perf_counter()
     launches = L.damgpu_launch_count() - l0
+    L.damgpu_radix_totals(rtot, 1)
+    radix_bytes, radix_ms, radix_launches, radix_sorts = [float(x) for x in rtot]
     dev_ms = ev0.elapsed_time(ev1)
     wall_ms = (t1 - t0) * 1e3
     step_ms = max(dev_ms, wall_ms) / args.steps          # host-side syncs are part of the step
@@ -323,9 +397,9 @@ def main():
         total_bases = float(bases)
     value = total_bases / (step_ms / 1e3)
 
-    # ---- roofline kernel: k_radix_pass on the WHOLE reads list (Sort_Kmers as the reference does it:
-    # the form taken with -t, -m, more than two reference blocks, or when the list is asked for), timed
-    # live with CUDA events on the library's stream, the list (2.2 GB) far larger than L2
+    # ---- side region (NOT part of a step): k_radix_pass on the WHOLE reads list, Sort_Kmers as the
+    # reference does it -- the form taken with -t, -m, more than two reference blocks, or when the list
+    # is asked for -- timed live with CUDA events on the library's stream, the list (2.2 GB) far larger than L2
     if rank == 0:
         for it in range(2 + args.steps):
             ir = api.Index(dr)
@@ -357,84 +431,93 @@ def main():
         t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
-    h2d = int(hr.bases.size + 2 * hg.bases.size + hg.bases.size +
-              8 * (hr.boff.size + 3 * hg.boff.size) + 4 * (hr.rlen.size + 3 * hg.rlen.size))
+    # what one e2e step copies: the packed reads + their offsets, the reference block in both orientations
+    # and once more for the Reporter
+    h2d = int(hr.packed.size + 8 * hr.poff.size + 8 * hr.boff.size + 4 * hr.rlen.size
+              + 3 * hg.bases.size + 3 * (8 * hg.boff.size + 4 * hg.rlen.size))
     d2h = int(nbytes + 16 * hr.nreads)
 
     if rank == 0:
         peak, which = peaks()
         n = stats["kmers"]
         pass_ms = float(np.mean(sort_ms)) / max(sort_n, 1)
-        achieved = 32.0 * n / (pass_ms / 1e3) / 1e9
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "r01_radix_pass_traffic.json")) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
-        except Exception:
-            pass
+        achieved_full = 32.0 * n / (pass_ms / 1e3) / 1e9
+        traffic_full = profile_json("r01_radix_pass_traffic.json").get("dram_bytes_per_launch")
+        instep = profile_json("r02_radix_pass_in_step.json")
+        alnp = profile_json("r02_k_align_duo.json")
         rs = stats["report"]
+        in_ms = radix_ms / max(radix_launches, 1.0)
+        in_ach = radix_bytes / max(radix_ms, 1e-9) / 1e6          # bytes per ms -> GB/s
+        fe = float(np.mean([f["extract_ms"] for f in flt]))
+        jb = 2 * 16.0 * (stats["join_fwd"]["alen"] + stats["join_fwd"]["blen"])
+        jm = max(float(np.mean(join_ms)), 1e-9)
+        am = max(float(np.mean(aln_ms)), 1e-9)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "reads_per_gpu": int(hr.nreads), "read_bases_per_gpu": bases,
-                       "kmer": 20, "l2": "inputs larger than L2 (126 MB): the reads block is %.0f MB (1 byte per base), the whole k-mer "
-                             "list sorted in the roofline region %.1f GB; no flush between steps" % (bases / 1e6, 16.0 * n / 1e9),
-                       "index": "built on rank 0 and broadcast with NCCL" if world > 1 else "built locally"},
+            "config": config_of(hr.nreads, bases, n, "built on rank 0 and broadcast with NCCL" if bcast else "built locally"),
             "e2e": {"value": total_bases / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
-            "roofline": {"kernel": "k_radix_pass (one LSD pass over the whole reads k-mer list)", "bound": "hbm",
-                         "note": "timed in its own region after the steps: a step builds the reads list only "
-                                 "from the k-mers that occur in the reference block (roofline_filter), the "
-                                 "same pass kernel then runs on %d instead of %d records"
-                                 % (int(np.mean([f["survivors"] for f in flt])), n),
-                         "achieved": achieved, "peak": peak, "peak_source": which + " copy bandwidth, burst",
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "algorithmic_bytes_per_launch": 32 * n, "avg_launch_ms": pass_ms,
-                         "launches_per_step": sort_n},
+            # the HBM-bound kernel of the timed path: every k_radix_pass launch of the timed steps (reference
+            # lists of both orientations, the surviving reads k-mers, the seed lists), CUDA events around the
+            # passes of each sort on the launching stream.  Lists of 4-9 M records: a pass is 25-45 us.
+            "roofline": {"kernel": "k_radix_pass, all launches inside the timed steps", "bound": "hbm",
+                         "achieved": in_ach, "peak": peak, "peak_source": which + " copy bandwidth, burst",
+                         "unit": "GB/s", "frac": in_ach / peak,
+                         "traffic": instep.get("dram_bytes_per_launch"),
+                         "algorithmic_bytes_per_launch": radix_bytes / max(radix_launches, 1.0),
+                         "avg_launch_ms": in_ms,
+                         "launches_per_step": radix_launches / args.steps, "sorts_per_step": radix_sorts / args.steps,
+                         "share_of_step": radix_ms / args.steps / step_ms},
+            # the kernel that dominates the step; no byte roofline applies (integer ALU / dependent latency):
+            # furthest-reaching cells per second live, issue-slot / ALU-pipe / lane figures from the committed
+            # ncu capture of the same kernel on the same workload
+            "roofline_align": {"kernel": "k_align_duo + k_unwind", "bound": "issue slots / dependent latency",
+                               "ms": am, "share_of_step": am / step_ms,
+                               "cells_per_s": rs["ncells"] / (am / 1e3), "waves_per_s": rs["nwaves"] / (am / 1e3),
+                               "cells_per_wave": rs["ncells"] / max(rs["nwaves"], 1),
+                               "ncu": alnp},
+            # side region, not in a step (launches_per_step 0): the same pass kernel on the whole reads list
+            "roofline_sort_full": {"kernel": "k_radix_pass (one LSD pass over the whole reads k-mer list)", "bound": "hbm",
+                                   "note": "timed in its own region after the steps: a step builds the reads list only from "
+                                           "the k-mers that occur in the reference block (roofline_filter), %d of %d records"
+                                           % (int(np.mean([f["survivors"] for f in flt])), n),
+                                   "achieved": achieved_full, "peak": peak, "unit": "GB/s", "frac": achieved_full / peak,
+                                   "traffic": traffic_full, "algorithmic_bytes_per_launch": 32 * n,
+                                   "avg_launch_ms": pass_ms, "launches_per_step": 0},
             # merge-join of both orientations of a step: SURVEY 8(d) counts 16 B per input record per
             # scan; here the shorter list drives and finds its codes in the longer one through a prefix
             # table (built once per reads block), so the second call never scans the reads list
             "roofline_merge": {"kernel": "k_build_lut + k_join_match, both orientations of a step", "bound": "hbm",
-                               "algorithmic_bytes": 2 * 16 * (stats["join_fwd"]["alen"] + stats["join_fwd"]["blen"]),
-                               "ms": float(np.mean(join_ms)),
-                               "achieved": 2 * 16.0 * (stats["join_fwd"]["alen"] + stats["join_fwd"]["blen"])
-                                           / (max(float(np.mean(join_ms)), 1e-9) / 1e3) / 1e9,
-                               "peak": peak, "unit": "GB/s",
-                               "frac": 2 * 16.0 * (stats["join_fwd"]["alen"] + stats["join_fwd"]["blen"])
-                                       / (max(float(np.mean(join_ms)), 1e-9) / 1e3) / 1e9 / peak},
+                               "algorithmic_bytes": jb, "ms": jm, "achieved": jb / (jm / 1e3) / 1e9,
+                               "peak": peak, "unit": "GB/s", "frac": jb / (jm / 1e3) / 1e9 / peak},
             # the reads-side index of a step: hash bitmap of the reference codes (both orientations),
             # extraction with a membership test + ordered compaction, radix passes over the survivors.
-            # Bound by bitmap lookups in L2 (one 32-byte sector per k-mer), not by HBM: algorithmic bytes
-            # = 1 B per base + 16 B per survivor.
-            "roofline_filter": {"kernel": "k_extract_filtered", "bound": "l2 lookups",
-                                "ms": float(np.mean([f["extract_ms"] for f in flt])),
-                                "lookups_per_s": n / (max(float(np.mean([f["extract_ms"] for f in flt])), 1e-9) / 1e3),
+            # Bound by bitmap lookups in L2 (one 32-byte sector per k-mer), not by HBM.
+            "roofline_filter": {"kernel": "k_extract_filtered", "bound": "l2 lookups", "ms": fe,
+                                "lookups_per_s": n / (max(fe, 1e-9) / 1e3),
                                 "survivors": int(np.mean([f["survivors"] for f in flt])), "kmers": n,
                                 "algorithmic_bytes": int(bases + hr.nreads + 16 * np.mean([f["survivors"] for f in flt]))},
-            # the same pass kernel where a step runs it on rank 0: the forward reference list of the step
-            # (launch-bound at this size: a pass is ~25 us), timed live inside the timed region
-            "roofline_in_step": {"kernel": "k_radix_pass on the forward reference list inside the timed steps",
-                                 "bound": "hbm", "records": int(stats["ref_kmers"]),
-                                 "avg_launch_ms": float(np.mean([r["sort_ms"] / max(r["npass"], 1) for r in rsort])),
-                                 "achieved": 32.0 * stats["ref_kmers"] / (max(float(np.mean([r["sort_ms"] / max(r["npass"], 1) for r in rsort])), 1e-9) / 1e3) / 1e9,
-                                 "peak": peak, "unit": "GB/s",
-                                 "frac": 32.0 * stats["ref_kmers"] / (max(float(np.mean([r["sort_ms"] / max(r["npass"], 1) for r in rsort])), 1e-9) / 1e3) / 1e9 / peak},
             "phases_ms": {"ref_bitmap": float(np.mean([f["bitmap_ms"] for f in flt])),
-                          "extract_filtered": float(np.mean([f["extract_ms"] for f in flt])),
+                          "extract_filtered": fe,
                           "radix_sort_survivors": float(np.mean([f["sort_ms"] for f in flt])),
-                          "align_kernel": float(np.mean(aln_ms)),
+                          "radix_passes_in_step": radix_ms / args.steps,
+                          "align_kernel": am,
                           "full_sort_extract": float(np.mean(ext_ms)), "full_sort_radix": float(np.mean(sort_ms))},
-            "extension": {"cells_per_s": rs["ncells"] / (max(float(np.mean(aln_ms)), 1e-9) / 1e3),
+            "extension": {"cells_per_s": rs["ncells"] / (am / 1e3),
                           "waves": rs["nwaves"], "alignments": rs["nalign"], "records": int(nrec)},
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
-                out["cpu_baseline"] = cpu_baseline()
+                wp, cpu = whole_process(contigs, rb, rl, local)
+                if wp is not None:
+                    out["whole_process"] = wp
+                    out["cpu_baseline"] = cpu
             except Exception as e:                       # the baseline must not take the line down
-                out["cpu_baseline"] = {"error": str(e)[:200]}
+                out["cpu_baseline"] = {"error": str(e)[:300]}
         os.write(real_out, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.barrier()

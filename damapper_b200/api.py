@@ -24,7 +24,8 @@ class CBlock(C.Structure):
     _fields_ = [("bases", C.c_void_p), ("boff", C.c_void_p), ("rlen", C.c_void_p),
                 ("nreads", C.c_int32), ("tfirst", C.c_int32), ("maxlen", C.c_int32),
                 ("totlen", C.c_int64), ("sizeof_db", C.c_int64),
-                ("mask_off", C.c_void_p), ("mask_pts", C.c_void_p)]
+                ("mask_off", C.c_void_p), ("mask_pts", C.c_void_p),
+                ("packed", C.c_void_p), ("poff", C.c_void_p), ("packed_bytes", C.c_int64)]
 
 
 class COptions(C.Structure):
@@ -48,6 +49,7 @@ SYMBOLS = {
     "damgpu_device_memory": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "damgpu_time_kernels": (None, [C.c_int]),
     "damgpu_set_align_tier": (None, [C.c_int, C.c_int]),
+    "damgpu_radix_totals": (None, [C.POINTER(C.c_double), C.c_int]),
     "damgpu_last_sort_times": (None, [C.POINTER(C.c_float)]),
     "damgpu_last_join_times": (None, [C.POINTER(C.c_float)]),
     "damgpu_Set_Filter_Params": (C.c_int, [C.c_int, C.c_int, C.c_int]),
@@ -83,6 +85,7 @@ SYMBOLS = {
     "damgpu_mapper_match": (None, [_P, _P, _P, C.c_int, C.c_int]),
     "damgpu_mapper_chain": (None, [_P, _P, C.c_int, C.c_int, C.c_int]),
     "damgpu_mapper_last_hits": (C.c_int64, [_P]),
+    "damgpu_mapper_last_limit": (C.c_int, [_P]),
     "damgpu_mapper_num_candidates": (C.c_int64, [_P]),
     "damgpu_mapper_get_candidates": (C.c_int64, [_P, _P, _P, _P, C.c_int64]),
     "damgpu_mapper_get_cover": (C.c_int64, [_P, _P, C.c_int64]),
@@ -146,7 +149,16 @@ class HostBlock:
         self.c = CBlock(self.bases.ctypes.data + 1, self.boff.ctypes.data, self.rlen.ctypes.data,
                         self.nreads, tfirst, self.maxlen, self.totlen, self.sizeof_db,
                         self.mask_off.ctypes.data if mask is not None else None,
-                        self.mask_pts.ctypes.data if mask is not None else None)
+                        self.mask_pts.ctypes.data if mask is not None else None, None, None, 0)
+
+    def attach_packed(self, packed: np.ndarray, poff: np.ndarray):
+        """Give the block its .bps image (pack_bps): layer 1 then uploads 2 bits per base."""
+        self.packed = packed if packed.dtype == np.uint8 and packed.flags.c_contiguous else np.ascontiguousarray(packed, dtype=np.uint8)
+        self.poff = np.ascontiguousarray(poff, dtype=np.int64)
+        self.c.packed = self.packed.ctypes.data
+        self.c.poff = self.poff.ctypes.data
+        self.c.packed_bytes = int(self.packed.size)
+        return self
 
 
 def set_filter_params(kmer: int = 20, suppress: int = 0, nthreads: int = 4) -> int:
@@ -418,6 +430,8 @@ def map_block(reads: HostBlock, ref_blocks, wholeref: HostBlock, kmer=20, suppre
         dg.complement()
         ig = Index(dg)
         m.match(dg, ig, 1, 0)
+        limit = load().damgpu_mapper_last_limit(m.h)
+        deferred = ir.is_deferred
         ig.free()
         dg.free()
     cands = m.candidates() if want_candidates else None
@@ -425,7 +439,7 @@ def map_block(reads: HostBlock, ref_blocks, wholeref: HostBlock, kmer=20, suppre
     dw = DeviceBlock(wholeref)
     rep = m.report(dw, ave_corr, spacing, freq, (1 if do_a else 0) | (2 if do_b else 0))
     out = dict(a=rep.a, anrec=rep.records(0), b=rep.b, bnrec=rep.records(1), prof=rep.prof,
-               stats=rep.stats(), candidates=cands, cover=cover)
+               stats=rep.stats(), candidates=cands, cover=cover, limit=limit, deferred=deferred)
     rep.free(); dw.free(); m.free(); ir.free(); dr.free()
     set_reads_filter("auto")
     return out

@@ -153,8 +153,11 @@ static void need_gpu()
 }
 
 static DeviceBlock *upload(const damgpu_block *b)
-{ DeviceBlock *blk = upload_block(b->bases, b->boff, b->rlen, b->nreads, b->tfirst, b->maxlen,
-                                  b->totlen, b->sizeof_db, 0);
+{ DeviceBlock *blk = (b->packed != nullptr && b->poff != nullptr)
+      ? upload_block_packed(b->packed, b->poff, b->packed_bytes, b->boff, b->rlen, b->nreads,
+                            b->tfirst, b->maxlen, b->totlen, b->sizeof_db, 0)
+      : upload_block(b->bases, b->boff, b->rlen, b->nreads, b->tfirst, b->maxlen,
+                     b->totlen, b->sizeof_db, 0);
   set_block_mask(blk, b->mask_off, b->mask_pts, 0);
   return blk;
 }
@@ -228,6 +231,7 @@ void damgpu_set_align_tier(int tier, int slots)
   (void) slots;
 }
 void damgpu_last_join_times(float out[4]) { join_times(out); }
+void damgpu_radix_totals(double out[4], int reset) { radix_totals(out, reset); }
 void damgpu_last_sort_times(float out[3]) { out[0] = g_sort_times[0]; out[1] = g_sort_times[1]; out[2] = g_sort_times[2]; }
 
 int damgpu_Set_Filter_Params(int kmer, int suppress, int nthreads)   // map.c:124-150
@@ -415,6 +419,9 @@ void damgpu_mapper_match(damgpu_mapper *mm, const damgpu_dblock *ref, const damg
 
 int64_t damgpu_mapper_last_hits(const damgpu_mapper *mm)
 { return reinterpret_cast<const MapperH *>(mm)->m->last_nhits; }
+int damgpu_mapper_last_limit(const damgpu_mapper *mm)
+{ return reinterpret_cast<const MapperH *>(mm)->m->last_limit; }
+
 
 // host copies of the candidate pool, walked per read (newest first, as the lists are linked)
 static void fetch_pool(const Mapper *m, std::vector<Candidate> &cand, std::vector<int> &head,

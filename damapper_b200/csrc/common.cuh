@@ -73,6 +73,8 @@ extern bool g_chain_async;         // chain kernel on its own stream (DAMGPU_SYN
 // Sorts ping-pong between a and b and returns the buffer holding the result.
 void *radix_sort16(void *a, void *b, uint32_t n, const int *bytes, int npass, uint32_t *hist,
                    cudaStream_t stream);
+// bytes / ms / pass launches / calls of the sorts since the last reset (damgpu_time_kernels on)
+void radix_totals(double out[4], int reset);
 // histogram of all pass bytes in one read of the array
 void radix_histogram(const void *recs, uint32_t n, const int *bytes, int npass, uint32_t *hist,
                      cudaStream_t stream);

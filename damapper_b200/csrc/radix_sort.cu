@@ -6,6 +6,7 @@
 // Replaces lex_sort/lex_thread of the reference (map.c:181-444).  The reference sorts the
 // key bytes flagged in bytes[16], least significant first, with a stable scatter; any
 // stable LSD sort over the same bytes yields the same array (SURVEY.md section 4 items 1,2).
+#include <vector>
 #include "common.cuh"
 
 namespace damgpu {
@@ -341,6 +342,24 @@ void radix_histogram(const void *recs, uint32_t n, const int *bytes, int npass, 
          (const uint4 *) recs, n, pb, hist);
 }
 
+// With damgpu_time_kernels on, every sort leaves a pair of events around its passes; radix_totals()
+// resolves them: bytes (32 per record and pass), ms, pass launches and calls since the last reset.
+struct PendingSort { cudaEvent_t e0, e1; double bytes; int npass; };
+static std::vector<PendingSort> g_pending;
+static double g_tot[4] = { 0., 0., 0., 0. };
+
+void radix_totals(double out[4], int reset)
+{ for (PendingSort &p : g_pending)
+    { float ms = 0.f;
+      if (cudaEventSynchronize(p.e1) == cudaSuccess && cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess)
+        { g_tot[0] += p.bytes; g_tot[1] += ms; g_tot[2] += p.npass; g_tot[3] += 1; }
+      cudaEventDestroy(p.e0); cudaEventDestroy(p.e1);
+    }
+  g_pending.clear();
+  for (int i = 0; i < 4; i++) out[i] = g_tot[i];
+  if (reset) g_tot[0] = g_tot[1] = g_tot[2] = g_tot[3] = 0.;
+}
+
 void *radix_sort16(void *a, void *b, uint32_t n, const int *bytes, int npass, uint32_t *hist,
                    cudaStream_t stream)
 { if (n == 0 || npass == 0)
@@ -348,8 +367,10 @@ void *radix_sort16(void *a, void *b, uint32_t n, const int *bytes, int npass, ui
   if (n >= (1u << 30))
     fatal("radix_sort16: %u records exceed the 2^30 limit of the 32-bit look-back words", n);
   const uint32_t ntiles = (n + RS_TILE - 1) / RS_TILE;
-  uint32_t *state = dalloc<uint32_t>((size_t) ntiles * 256 + 1);
-  uint32_t *counter = state + (size_t) ntiles * 256;
+  // tile states + ticket counter of EVERY pass, cleared by one memset (a memset per pass is a launch
+  // per pass: on the 5-10 M record lists of a step the passes are 25-45 us each)
+  const size_t per_pass = (size_t) ntiles * 256 + 1;
+  uint32_t *state = dalloc<uint32_t>(per_pass * (size_t) npass);
 
   static int attr_set = -1;
   if (attr_set != (int) g_radix_reload)
@@ -361,12 +382,23 @@ void *radix_sort16(void *a, void *b, uint32_t n, const int *bytes, int npass, ui
       attr_set = (int) g_radix_reload;
     }
   LAUNCH(k_radix_prefix, npass, 256, 0, stream, hist);
+  CUDA_CHECK(cudaMemsetAsync(state, 0, sizeof(uint32_t) * per_pass * (size_t) npass, stream));
+  PendingSort ps;
+  if (g_time_kernels)
+    { cudaEventCreate(&ps.e0); cudaEventCreate(&ps.e1);
+      ps.bytes = 32. * (double) n * npass; ps.npass = npass;
+      cudaEventRecord(ps.e0, stream);
+    }
   uint4 *src = (uint4 *) a, *dst = (uint4 *) b;
   for (int p = 0; p < npass; p++)
-    { CUDA_CHECK(cudaMemsetAsync(state, 0, sizeof(uint32_t) * ((size_t) ntiles * 256 + 1), stream));
+    { uint32_t *st = state + per_pass * (size_t) p;
       LAUNCH(radix_pass_for(bytes[p]), ntiles, RS_THREADS, RS_SMEM, stream, src, dst, n,
-             0x4440u | (uint32_t) (bytes[p] & 3), hist + p * 256, state, counter, (uint32_t) g_radix_pf);
+             0x4440u | (uint32_t) (bytes[p] & 3), hist + p * 256, st, st + (size_t) ntiles * 256, (uint32_t) g_radix_pf);
       uint4 *t = src; src = dst; dst = t;
+    }
+  if (g_time_kernels)
+    { cudaEventRecord(ps.e1, stream);
+      g_pending.push_back(ps);
     }
   dfree(state);                                        // stream-ordered reuse (cache_alloc)
   return src;

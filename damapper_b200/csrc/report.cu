@@ -705,6 +705,8 @@ k_check_trace(const uint8_t *__restrict__ dense, const int64_t *__restrict__ off
     atomicAdd(fails, (unsigned long long) bad);
 }
 
+__global__ void k_flip_byte(uint8_t *p) { *p = (uint8_t) (*p + 1); }   // DAMGPU_TEST_CORRUPT_TRACE (tests only)
+
 template <typename T> static std::vector<T> d2h(const T *d, size_t n)
 { std::vector<T> v(n);
   if (n) CUDA_CHECK(cudaMemcpy(v.data(), d, sizeof(T) * n, cudaMemcpyDeviceToHost));
@@ -959,6 +961,8 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
         dstv.resize((size_t) tot);
         if (tot > 0)
           CUDA_CHECK(cudaMemcpyAsync(dstv.data(), dense, (size_t) tot, cudaMemcpyDeviceToHost, stream));
+        if (fam == 0 && tot > 48 && getenv("DAMGPU_TEST_CORRUPT_TRACE") != nullptr)
+          LAUNCH(k_flip_byte, 1, 1, 0, stream, dense + 41);    // test hook: a record the checker must reject
         if (n > 0 && tot > 0)
           LAUNCH(k_check_trace, (n + 255) / 256, 256, 0, stream, dense, d_off, fam ? R.nrec_b : R.nrec_a, n,
                  S, (S <= 125) ? 1 : 2, d_ull + 8);       // TRACE_XOVR, align.h:45

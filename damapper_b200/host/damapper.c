@@ -13,6 +13,13 @@
  * the whole reference the Reporter aligns against -- resident in HBM for the reads blocks that
  * follow, as long as they fit in DAMGPU_REF_CACHE (default 45 %) of the device memory; the next
  * reads block is read from disk by a helper thread while the GPU maps the current one.
+ *
+ * -G<n> (not in the reference): n GPUs of the box.  Reads blocks are independent (damapper.c:825-914:
+ * nothing is carried from one to the next), so the driver forks n workers BEFORE CUDA is touched, worker
+ * r takes blocks r, r+n, ... of the command line on the r-th device (DAMGPU_DEVICES="3,5,..." picks
+ * them; default 0..n-1) with CUDA_VISIBLE_DEVICES narrowed to it, in its own sort directory; each
+ * builds the reference indices for itself (on a B200 a 250 Mbp block is indexed in ~10 ms per strand,
+ * about what moving the 4 GB list over NVLink costs).  The parent only waits.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -23,13 +30,15 @@
 #include <sys/types.h>
 #include <time.h>
 #include <pthread.h>
+#include <sys/mman.h>
+#include <sys/wait.h>
 #include "dazz_db.h"
 
 static const char *Prog_Name = "damapper";
 static char *SORT_PATH = "/tmp";
 
 static const char *Usage[] =
-  { "[-vpzCN] [-k<int(20)>] [-t<int>] [-M<int>] [-T<int(4)>] [-P<dir(/tmp)>]",
+  { "[-vpzCN] [-k<int(20)>] [-t<int>] [-M<int>] [-T<int(4)>] [-P<dir(/tmp)>] [-G<int(1)>]",
     "         [-e<double(.85)] [-s<int(100)>] [-n<double(1.00)>]",
     "         [-m<track>]+  <reference:dam> <reads:db> ...",
   };
@@ -163,6 +172,8 @@ static void prefetch_wait(Prefetch *p)
 int main(int argc, char *argv[])
 { int    VERBOSE = 0, PROFILE = 0, COVER = 0, NOMAP = 0, MAP_ORDER = 1;
   int    KMER_LEN = 20, MAX_REPS = 0, NTHREADS = 4, SPACING = 100, MTOP = 0;
+  int    NGPUS = 1, RANK = 0;
+  int   *MSHARED = NULL;                                  /* -G: mask-use flags of all workers */
   double AVE_ERROR = .85, BEST_TIE = 1.0;
   uint64_t MEM_PHYSICAL, MEM_LIMIT;
   int    mflag, i, j, k;
@@ -252,6 +263,9 @@ int main(int argc, char *argv[])
         case 'T':
           NTHREADS = arg_int(argv[i],"Number of threads",1);
           break;
+        case 'G':
+          NGPUS = arg_int(argv[i],"Number of GPUs",1);
+          break;
       }
     else
       argv[j++] = argv[i];
@@ -272,6 +286,7 @@ int main(int argc, char *argv[])
       fprintf(stderr,"\n");
       fprintf(stderr,"      -T: Use -T threads (here: number of per-range .las files).\n");
       fprintf(stderr,"      -P: Do sorts and merges in directory -P.\n");
+      fprintf(stderr,"      -G: Map the reads blocks on -G GPUs of this box, round robin.\n");
       fprintf(stderr,"      -m: Soft mask the blocks with the specified mask.\n");
       fprintf(stderr,"\n");
       fprintf(stderr,"      -v: Verbose mode, output statistics as proceed.\n");
@@ -316,6 +331,75 @@ int main(int argc, char *argv[])
   spec.trace_space = SPACING;
   memcpy(spec.freq,refdb.freq,sizeof(spec.freq));
 
+  /* -G: one worker process per GPU, forked before anything touches CUDA */
+  if (NGPUS > argc-2)
+    NGPUS = argc-2;
+  if (NGPUS > 1)
+    { pid_t kids[64];
+      char  devs[64][16];
+      const char *list = getenv("DAMGPU_DEVICES");
+      int   r, st, bad = 0;
+      if (NGPUS > 64) NGPUS = 64;
+      for (r = 0; r < NGPUS; r++)
+        snprintf(devs[r],sizeof(devs[r]),"%d",r);
+      if (list == NULL) list = getenv("CUDA_VISIBLE_DEVICES");
+      if (list != NULL)                                   /* r-th entry of the list */
+        { const char *p = list;
+          for (r = 0; r < NGPUS && *p != '\0'; r++)
+            { size_t n = strcspn(p,",");
+              if (n >= sizeof(devs[r])) n = sizeof(devs[r])-1;
+              memcpy(devs[r],p,n); devs[r][n] = '\0';
+              p += n; if (*p == ',') p++;
+            }
+          if (r < NGPUS)
+            { fprintf(stderr,"%s: -G%d but only %d devices in '%s'\n",Prog_Name,NGPUS,r,list);
+              exit (1);
+            }
+        }
+      MSHARED = (int *) mmap(NULL,sizeof(int)*256,PROT_READ|PROT_WRITE,MAP_SHARED|MAP_ANONYMOUS,-1,0);
+      if (MSHARED == MAP_FAILED)
+        MSHARED = NULL;
+      else
+        memset(MSHARED,0,sizeof(int)*256);
+      fflush(NULL);
+      for (r = 0; r < NGPUS; r++)
+        { kids[r] = fork();
+          if (kids[r] < 0)
+            { fprintf(stderr,"%s: cannot fork worker %d\n",Prog_Name,r);
+              exit (1);
+            }
+          if (kids[r] == 0)
+            { RANK = r;
+              setenv("CUDA_VISIBLE_DEVICES",devs[r],1);
+              unsetenv("DAMGPU_DEVICE");
+              break;
+            }
+        }
+      if (r == NGPUS)                                     /* the parent: wait, report, leave */
+        { for (r = 0; r < NGPUS; r++)
+            if (waitpid(kids[r],&st,0) < 0 || !WIFEXITED(st) || WEXITSTATUS(st) != 0)
+              bad = 1;
+          if (!bad && MSHARED != NULL)
+            for (j = 0; j < MTOP; j++)
+              if (MSHARED[j] == 0)
+                printf("%s: Warning: Track %s given but never used.\n",Prog_Name,MASK[j]);
+          exit (bad);
+        }
+    }
+  else
+    { /* one device: do not make cuInit enumerate the others */
+      const char *dev = getenv("DAMGPU_DEVICE");
+      if (dev != NULL && getenv("CUDA_VISIBLE_DEVICES") == NULL)
+        { setenv("CUDA_VISIBLE_DEVICES",dev,1);
+          unsetenv("DAMGPU_DEVICE");
+        }
+    }
+
+  /* the first reads block comes off the disk while the CUDA context is created */
+  memset(&pre,0,sizeof(pre));
+  if (2+RANK < argc)
+    prefetch_start(&pre,argv[2+RANK],MASK,MTOP,Prog_Name);
+
   { const char *dev = getenv("DAMGPU_DEVICE");
     if (damgpu_init(dev ? atoi(dev) : -1) != 0)
       { fprintf(stderr,"%s: no usable CUDA device (%s); this build has no CPU path\n",
@@ -346,18 +430,14 @@ int main(int argc, char *argv[])
   { uint64_t fr = 0, tot = 0;
     const char *e = getenv("DAMGPU_REF_CACHE");           /* percent of HBM, 0 = as the reference */
     double pct = (e != NULL) ? atof(e) : 45.;
-    if (rcache != NULL && argc > 3 && pct > 0. && damgpu_device_memory(&fr,&tot) == 0)
+    if (rcache != NULL && 2+RANK+NGPUS < argc && pct > 0. && damgpu_device_memory(&fr,&tot) == 0)
       cache_budget = (uint64_t) (tot * (pct < 90. ? pct : 90.) / 100.);
   }
   /* the DALIGNER post-processing programs, or the built-in stand-in when they are not installed */
   builtin_sort = (getenv("DAMGPU_BUILTIN_SORT") != NULL || !on_path("LAsort"));
   if (builtin_sort && VERBOSE)
     printf("\n  LAsort is not on PATH (or DAMGPU_BUILTIN_SORT is set): built-in sort and merge of the .las files\n");
-  memset(&pre,0,sizeof(pre));
-  if (argc > 2)
-    prefetch_start(&pre,argv[2],MASK,MTOP,Prog_Name);
-
-  for (i = 2; i < argc; i++)                              /* damapper.c:825-914 */
+  for (i = 2+RANK; i < argc; i += NGPUS)                  /* damapper.c:825-914 */
     { char *broot, *aroot = refdb.root, name[4096], command[16384];
       damgpu_block  bview, aview;
       damgpu_dblock *dreads, *dref;
@@ -391,8 +471,8 @@ int main(int argc, char *argv[])
         printf("\nBuilding index for %s\n",broot);
       dreads = damgpu_block_upload_packed(&bview,bblock.packed,bblock.poff,bblock.packed_bytes);
       tick("upload reads block");
-      if (i+1 < argc)                                    /* the disk works while the GPU does */
-        prefetch_start(&pre,argv[i+1],MASK,MTOP,Prog_Name);
+      if (i+NGPUS < argc)                                /* the disk works while the GPU does */
+        prefetch_start(&pre,argv[i+NGPUS],MASK,MTOP,Prog_Name);
       /* one or two reference blocks: the reads list is built per block from the k-mers that occur in
          it (deferred); more: sorted once in full */
       bindex = (refdb.nblocks <= 2) ? damgpu_index_build_deferred(dreads) : damgpu_index_build(dreads);
@@ -540,7 +620,9 @@ int main(int argc, char *argv[])
     }
 
   for (j = 0; j < MTOP; j++)                              /* damapper.c:916-918 */
-    if (MSTAT[j] == 0)
+    if (MSHARED != NULL)
+      { if (MSTAT[j]) MSHARED[j] = 1; }                   /* -G: the parent prints what no worker used */
+    else if (MSTAT[j] == 0)
       printf("%s: Warning: Track %s given but never used.\n",Prog_Name,MASK[j]);
 
   Clean_Exit(0);

@@ -282,6 +282,7 @@ void dazz_view(const Dazz_Block *db, damgpu_block *v)
   v->maxlen = db->maxlen;
   v->totlen = db->totlen;
   v->mask_off = db->mask_off; v->mask_pts = db->mask_pts;
+  v->packed = NULL; v->poff = NULL; v->packed_bytes = 0;
   /* sizeof_DB, DB.c:1044-1051: sizeof(DAZZ_DB)=112, sizeof(DAZZ_READ)=40 */
   v->sizeof_db = 112 + 40*((int64_t) db->nreads+2) + db->path_len + 1 + (db->totlen + db->nreads + 4);
 }

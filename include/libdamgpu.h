@@ -48,6 +48,13 @@ typedef struct {
    * touch a masked base are not indexed (tuple_thread, map.c:481-543).  NULL = no mask. */
   const int64_t *mask_off;  /* nreads+1 entries, or NULL */
   const int32_t *mask_pts;
+  /* Optional: the reads as the .bps file holds them (Compress_Read, DB.c:319-340: four bases per byte,
+   * first base in the two top bits; read i starts at packed[poff[i]]).  When `packed` is not NULL the
+   * library uploads these bytes (a quarter of the volume) and expands them on the device, and `bases`
+   * may be NULL; boff/rlen still describe the Load_All_Reads image (DB.c:1389-1441). */
+  const uint8_t *packed;
+  const int64_t *poff;      /* nreads entries */
+  int64_t  packed_bytes;
 } damgpu_block;
 
 /* The globals map.h:16-23 declares extern and damapper.c:58-65 defines. */
@@ -87,6 +94,10 @@ void damgpu_time_kernels(int on);                     /* record per-phase CUDA-e
    0 = a warp per candidate (the tier that also re-runs what outgrows the first); `slots` is
    ignored; both yield the same records (Local_Alignment, align.c:1727-1946) */
 void damgpu_set_align_tier(int tier, int slots);
+/* every radix sort since the last reset (with damgpu_time_kernels on): [0]=algorithmic bytes (32 per
+ * record and pass), [1]=ms of the passes (CUDA events on the launching stream), [2]=pass
+ * launches, [3]=sorts */
+void damgpu_radix_totals(double out[4], int reset);
 /* ms of the last Sort_Kmers: [0]=extraction kernel, [1]=all radix passes, [2]=#passes */
 void damgpu_last_sort_times(float out[3]);
 /* of the last merge-join (with damgpu_time_kernels on): [0]=ms of the prefix table build (0 when the
@@ -180,6 +191,7 @@ void           damgpu_mapper_match(damgpu_mapper *m, const damgpu_dblock *ref,
 void           damgpu_mapper_chain(damgpu_mapper *m, const damgpu_seeds *s, int bstart, int comp,
                                    int start);
 int64_t        damgpu_mapper_last_hits(const damgpu_mapper *m);
+int            damgpu_mapper_last_limit(const damgpu_mapper *m);   /* the k-mer hit cap of the last match (map.c:2992-3052) */
 int64_t        damgpu_mapper_num_candidates(const damgpu_mapper *m);
 /* candidates in (read, list order); jcnt[i] pairs per candidate, jumps = (da,db) int32 pairs;
  * returns the total number of pairs (call with jumps = NULL to size) */

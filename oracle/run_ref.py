@@ -31,10 +31,11 @@ def _thread_sorted(files):
     return sorted(files, key=key)
 
 
-def run_damapper(workdir: str, ref: str, reads: str, flags=(), threads: int = 4, timeout=3600):
-    """Run `damapper <flags> -T<threads> ref reads` in `workdir`.
+def run_damapper(workdir: str, ref: str, reads: str, flags=(), threads: int = 4, timeout=3600, exe=None, env_extra=None):
+    """Run `damapper <flags> -T<threads> ref reads` in `workdir` (exe: another binary that keeps the
+    reference command line: oracle/_ref/damapper_timed, oracle/_ref/damapper_gpu, damapper_b200/damapper).
 
-    Returns dict(wall_s, m_files, r_files, prof_anno, prof_data, stdout)."""
+    Returns dict(wall_s, core_s, m_files, r_files, prof_anno, prof_data, stdout)."""
     keep = os.path.join(workdir, "keep")
     os.makedirs(keep, exist_ok=True)
     for f in glob.glob(os.path.join(keep, "*.las")):
@@ -44,7 +45,9 @@ def run_damapper(workdir: str, ref: str, reads: str, flags=(), threads: int = 4,
     env["DAMAPPER_KEEP_DIR"] = keep
     sortdir = os.path.join(workdir, "tmp")
     os.makedirs(sortdir, exist_ok=True)
-    cmd = [REF_BIN, "-T%d" % threads, "-P" + sortdir] + list(flags) + [ref, reads]
+    if env_extra:
+        env.update(env_extra)
+    cmd = [exe or REF_BIN, "-T%d" % threads, "-P" + sortdir] + list(flags) + [ref, reads]
     t0 = time.perf_counter()
     p = subprocess.run(cmd, cwd=workdir, env=env, capture_output=True, text=True, timeout=timeout)
     wall = time.perf_counter() - t0
@@ -58,7 +61,8 @@ def run_damapper(workdir: str, ref: str, reads: str, flags=(), threads: int = 4,
             rroot = rroot[: -len(ext)]
     anno = os.path.join(workdir, "." + rroot + ".prof.anno")
     data = os.path.join(workdir, "." + rroot + ".prof.data")
-    return dict(wall_s=wall, m_files=m_files, r_files=r_files,
+    core = re.search(r"\[core\] ([0-9.]+) s", p.stderr or "")
+    return dict(wall_s=wall, core_s=float(core.group(1)) if core else None, m_files=m_files, r_files=r_files,
                 prof_anno=anno if os.path.exists(anno) else None,
                 prof_data=data if os.path.exists(data) else None,
                 stdout=p.stdout, stderr=p.stderr)

@@ -1,0 +1,126 @@
+"""GPU parity at the sizes where the policies switch: the checker is the
+UNMODIFIED reference (oracle/_ref/damapper -T<cores>), run on the same databases; every byte of the
+per-thread .las streams and of the -p track is compared.  Each test asserts which path it exercised."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, base_freq
+
+pytestmark = pytest.mark.gpu
+
+
+def _threads():
+    t, c = 1, os.cpu_count() or 1
+    while 2 * t <= c:
+        t *= 2
+    return min(t, 16)
+
+
+def _ref_streams(wd, flags, threads):
+    from damapper_b200 import las
+    from oracle import run_ref
+    r = run_ref.run_damapper(wd, "ref.dam", "reads.db", flags=flags, threads=threads, timeout=3000)
+    a = las.canonical_stream(r["m_files"]) if r["m_files"] else b""
+    b = las.canonical_stream(r["r_files"]) if r["r_files"] else b""
+    prof = open(r["prof_data"], "rb").read() if r["prof_data"] else b""
+    return a, b, prof
+
+
+@pytest.fixture(scope="module")
+def api():
+    from damapper_b200 import api as a
+    from conftest import install_fatal_hook
+    a.init(0)
+    install_fatal_hook(a)
+    return a
+
+
+def test_c3_tenth_scale_repeat_rich(api, tmp_path):
+    """C3 at 0.1 (10 Mbp repeat-rich reference, 5 000 reads) with -n.95 -p -C: repeat families dense enough
+    for the k-mer hit cap (limit < 10000 under -M1), the general path of the chain kernel and many
+    alignments per read.  API with the deferred (filtered) reads index against the reference binary."""
+    from damapper_b200 import dazzdb, synth
+    from oracle import run_ref
+    if not run_ref.have_ref():
+        pytest.skip("oracle/_ref is not built")
+    contigs, rb, rl = synth.make_config("C3", scale=0.1, seed=71)
+    wd = str(tmp_path)
+    dazzdb.write_db(os.path.join(wd, "ref.dam"), contigs, is_dam=True)
+    dazzdb.write_db(os.path.join(wd, "reads.db"), (rb, rl))
+    want = _ref_streams(wd, ("-M1", "-n.95", "-p", "-C"), _threads())
+    rd = dazzdb.load_block((rb, rl)); rf = dazzdb.load_block(contigs)
+    hr, hf = api.HostBlock(*rd), api.HostBlock(*rf)
+    # the limit of map.c:2992-3052 depends on sizeof_DB of both blocks: path_len as the driver computes it
+    got = api.map_block(hr, [hf], hf, freq=base_freq(contigs), do_b=1, profile=1, best_tie=0.95,
+                        mem_limit=1 << 30, reads_filter="always")
+    assert got["limit"] < 10000, "the hit cap did not engage: %r" % (got.get("limit"),)
+    assert got["a"] == want[0], "M records differ"
+    assert got["b"] == want[1], "R records differ"
+    assert got["prof"] == want[2], "-p track differs"
+    assert got["anrec"] > 5000
+
+
+def test_c4_like_chromosome_scale_reference(tmp_path):
+    """A C4-like run through the two command lines: 250 Mbp reference (3 contigs, 250 M reference k-mers per
+    strand: the long-list paths of the sort and of the merge-join), 3 000 reads in 2 reads blocks."""
+    import glob
+    import subprocess
+    from damapper_b200 import dazzdb, las, synth
+    from oracle import run_ref
+    if not run_ref.have_ref():
+        pytest.skip("oracle/_ref is not built")
+    G = 250_000_000
+    genome = synth.make_genome(G, seed=72)
+    cuts = np.array([0, 100_000_000, 180_000_000, G])
+    rb, rl, _ = synth.make_reads(genome, 3000, seed=73, contig_bounds=cuts)
+    wd = str(tmp_path)
+    w = dazzdb.StreamDBWriter(os.path.join(wd, "ref.dam"), is_dam=True)
+    w.append(genome, np.diff(cuts)); w.close()
+    del genome
+    w = dazzdb.StreamDBWriter(os.path.join(wd, "reads.db"))
+    w.append(rb, rl); w.close(nblocks=2)
+    exe = os.path.join(ROOT, "damapper_b200", "damapper")
+
+    def run(binary, tag, env_extra=None):
+        keep = os.path.join(wd, "keep_" + tag); os.makedirs(keep)
+        tmp = os.path.join(wd, "tmp_" + tag); os.makedirs(tmp)
+        env = dict(os.environ, DAMAPPER_KEEP_DIR=keep, **(env_extra or {}))
+        env["PATH"] = os.path.join(run_ref.REF_DIR, "bin") + os.pathsep + env["PATH"]
+        p = subprocess.run([binary, "-T%d" % _threads(), "-P" + tmp, "-M64", "ref.dam", "reads.1", "reads.2"],
+                           cwd=wd, env=env, capture_output=True, text=True, timeout=3000)
+        assert p.returncode == 0, p.stderr[-2000:]
+        out = {}
+        for b in (1, 2):
+            m = run_ref._thread_sorted(glob.glob(os.path.join(keep, "reads.%d.ref.M[0-9]*.las" % b)))
+            out[b] = las.canonical_stream(m)
+        return out, p.stderr
+
+    got, err = run(exe, "gpu", {"DAMGPU_TIMING": "1"})
+    assert "match, both strands (cached)" in err, "the second reads block did not use the resident indices"
+    want, _ = run(run_ref.REF_BIN, "ref")
+    assert sum(len(v) for v in got.values()) > 500000
+    assert got == want
+
+
+def test_c5_full_size_chimeric_cover(api, tmp_path):
+    """C5 at 1.0 with -C -p: chimeric reads with 30 %-error stretches; bands wider than the 32-diagonal
+    window of the duo kernel are re-run by the warp kernel (overflow_jobs), both families compared."""
+    from damapper_b200 import dazzdb, synth
+    from oracle import run_ref
+    if not run_ref.have_ref():
+        pytest.skip("oracle/_ref is not built")
+    contigs, rb, rl = synth.make_config("C5", scale=1.0, seed=74)
+    wd = str(tmp_path)
+    dazzdb.write_db(os.path.join(wd, "ref.dam"), contigs, is_dam=True)
+    dazzdb.write_db(os.path.join(wd, "reads.db"), (rb, rl))
+    want = _ref_streams(wd, ("-M16", "-C", "-p"), _threads())
+    rd = dazzdb.load_block((rb, rl)); rf = dazzdb.load_block(contigs)
+    hr, hf = api.HostBlock(*rd), api.HostBlock(*rf)
+    got = api.map_block(hr, [hf], hf, freq=base_freq(contigs), do_b=1, profile=1, mem_limit=16 << 30)
+    assert got["a"] == want[0], "M records differ"
+    assert got["b"] == want[1], "R records differ"
+    assert got["prof"] == want[2], "-p track differs"
+    assert got["stats"]["trace_fails"] == 0
+    assert got["anrec"] > 10000
