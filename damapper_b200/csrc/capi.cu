@@ -542,11 +542,13 @@ int damgpu_report_write_las(const damgpu_report *rr, int family, const char *dir
       int64_t novl = 0;
       for (int64_t x = r0; x < r1; x++) novl += nrec[x];
       int ts = tspace;
-      fwrite(&novl, sizeof(int64_t), 1, f);
-      fwrite(&ts, sizeof(int), 1, f);
-      if (off[r1] > off[r0])
-        fwrite(v.data() + off[r0], 1, (size_t) (off[r1] - off[r0]), f);
-      fclose(f);
+      bool ok = (fwrite(&novl, sizeof(int64_t), 1, f) == 1) && (fwrite(&ts, sizeof(int), 1, f) == 1);
+      if (ok && off[r1] > off[r0])
+        { const size_t nb = (size_t) (off[r1] - off[r0]);
+          ok = (fwrite(v.data() + off[r0], 1, nb, f) == nb);
+        }
+      if (fclose(f) != 0) ok = false;
+      if (!ok) return 1;                                 // short write (full disk): the caller stops
     }
   return 0;
 }
@@ -556,18 +558,23 @@ int damgpu_report_write_profile(const damgpu_report *rr, const damgpu_block *rea
 { const ReportOut *r = reinterpret_cast<const ReportOut *>(rr);
   std::string base = std::string(dir) + "/." + aname + ".prof";
   FILE *af = fopen((base + ".anno").c_str(), "w"), *df = fopen((base + ".data").c_str(), "w");
-  if (af == nullptr || df == nullptr) return 1;
+  if (af == nullptr || df == nullptr)
+    { if (af != nullptr) fclose(af);
+      if (df != nullptr) fclose(df);
+      return 1;
+    }
   int size = sizeof(int64_t);
-  fwrite(&reads->nreads, sizeof(int), 1, af);
-  fwrite(&size, sizeof(int), 1, af);
+  bool ok = (fwrite(&reads->nreads, sizeof(int), 1, af) == 1) && (fwrite(&size, sizeof(int), 1, af) == 1);
   int64_t cnt = 0;
-  for (int a = 0; a < reads->nreads; a++)
-    { fwrite(&cnt, sizeof(int64_t), 1, af);
+  for (int a = 0; a < reads->nreads && ok; a++)
+    { ok = (fwrite(&cnt, sizeof(int64_t), 1, af) == 1);
       cnt += (reads->rlen[a] - 1) / tspace + 2;
     }
-  fwrite(&cnt, sizeof(int64_t), 1, af);
-  if (!r->prof.empty()) fwrite(r->prof.data(), 1, r->prof.size(), df);
-  fclose(af); fclose(df);
+  ok = ok && (fwrite(&cnt, sizeof(int64_t), 1, af) == 1);
+  if (ok && !r->prof.empty()) ok = (fwrite(r->prof.data(), 1, r->prof.size(), df) == r->prof.size());
+  if (fclose(af) != 0) ok = false;
+  if (fclose(df) != 0) ok = false;
+  if (!ok) return 1;
   return 0;
 }
 
@@ -595,8 +602,17 @@ void damgpu_Match_Filter(const damgpu_block *ablock, const damgpu_block *bblock,
                          int alen, void *btable, int blen, int comp, int start)
 { (void) ablock; (void) bblock;
   KmerIndex *ai = reinterpret_cast<KmerIndex *>(atable), *bi = reinterpret_cast<KmerIndex *>(btable);
+  if (ai != nullptr && ai->block == nullptr)
+    fatal("Match_Filter: the reads index was not made by damgpu_Sort_Kmers (it carries no block)");
   if (alen == 0 || blen == 0 || ai == nullptr || bi == nullptr)     // map.c:2955-2956
     { free_index(bi);
+      if (ai != nullptr && (g_mapper == nullptr || g_mapper_key != atable || start))
+        { // nothing to match, but the reads block is under way: Reporter writes its (empty) files
+          if (g_mapper) damgpu_mapper_free(reinterpret_cast<damgpu_mapper *>(g_mapper));
+          g_mapper = reinterpret_cast<MapperH *>(damgpu_mapper_new(reinterpret_cast<damgpu_dblock *>(ai->block),
+                                                                   reinterpret_cast<damgpu_index *>(ai)));
+          g_mapper_key = atable;
+        }
       return;
     }
   if (g_mapper == nullptr || g_mapper_key != atable)
@@ -614,8 +630,18 @@ void damgpu_Match_Filter(const damgpu_block *ablock, const damgpu_block *bblock,
 void damgpu_Reporter(const char *aname, const damgpu_block *ablock, const char *bname,
                      const damgpu_block *bblock, const damgpu_align_spec *spec, int mflag)
 { need_gpu();
+  DeviceBlock *ablk = nullptr;
+  KmerIndex   *aidx = nullptr;
   if (g_mapper == nullptr)
-    fatal("Reporter called before Match_Filter");
+    { // no Match_Filter call reached the core for this reads block (no k-mers on one side of every
+      // call, map.c:2955-2956): the reference goes on and writes empty files, so does this
+      if (ablock == nullptr)
+        fatal("Reporter called before Match_Filter");
+      ablk = upload(ablock);
+      aidx = sort_kmers_deferred(ablk, g_par.kmer, g_par.suppress, 0);
+      g_mapper = reinterpret_cast<MapperH *>(damgpu_mapper_new(reinterpret_cast<damgpu_dblock *>(ablk),
+                                                               reinterpret_cast<damgpu_index *>(aidx)));
+    }
   DeviceBlock *ref = upload(bblock);
   damgpu_report *rep = damgpu_mapper_report(reinterpret_cast<damgpu_mapper *>(g_mapper),
                                             reinterpret_cast<damgpu_dblock *>(ref), spec, mflag);
@@ -636,6 +662,8 @@ void damgpu_Reporter(const char *aname, const damgpu_block *ablock, const char *
   damgpu_report_free(rep);
   damgpu_mapper_free(reinterpret_cast<damgpu_mapper *>(g_mapper));
   g_mapper = nullptr; g_mapper_key = nullptr;
+  free_index(aidx);
+  free_block(ablk);
 }
 
 }  // extern "C"

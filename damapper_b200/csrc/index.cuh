@@ -20,6 +20,7 @@ struct DeviceBlock
   mutable int32_t *tile_tab = nullptr;   // first / last read of every 4096-position tile (kmer_filter.cu)
   int      nreads = 0, tfirst = 0, maxlen = 0;
   int64_t  totlen = 0, total = 0, sizeof_db = 0;
+  uint64_t uid = 0;             // identity of the block (kept by complement_block): key of the filtered reads list
   std::vector<int64_t> h_boff;
   std::vector<int32_t> h_rlen;
 };
@@ -40,7 +41,14 @@ struct KmerIndex
   const DeviceBlock *src = nullptr;  // block to extract from (must outlive the index)
   int      K = 0;
   KmerIndex *filt = nullptr;      // sub-list of the records whose code occurs in one reference block
-  unsigned long long filt_sig = 0;   // orientation-invariant signature of that reference list
+  // what `filt` was built for.  Exact key: the identity of the reference block (the driver complements
+  // a block in place, so both orientations carry the same uid).  A list of another block object (layer 1
+  // uploads the two orientations separately; an imported list has no block) is recognised by a 128-bit
+  // orientation-invariant multiset hash of its codes plus its length.
+  uint64_t filt_uid = 0, src_uid = 0;   // src_uid: uid of the block this list was built from (0: unknown)
+  unsigned long long *filt_dsig = nullptr;   // device: the two 64-bit sums of the list `filt` was built for
+  unsigned long long filt_sig[2] = { 0, 0 }; // host copy, fetched when first needed
+  bool     filt_sig_known = false;
   int      filt_blen = 0, nfilt = 0;
 };
 

@@ -64,24 +64,29 @@ __device__ __forceinline__ uint64_t rc_code(uint64_t c, int K)
   return (~x) & kmask;
 }
 
-// sig[0] += mix(canonical code) over the list (invariant under complementing the block);
-// with bitmap != null also sets the bits of every code and of its reverse complement
+// sig[0], sig[1] += two mixes of the canonical code over the list (invariant under complementing the
+// block); with bitmap != null also sets the bits of every code and of its reverse complement
 __global__ void __launch_bounds__(256)
 k_ref_bitmap(const KmerPos *__restrict__ B, int blen, int K, int hshift, unsigned long long *bitmap,
              unsigned long long *sig)
-{ unsigned long long s = 0;
+{ unsigned long long s = 0, s2 = 0;
   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < blen;
        i += (int64_t) gridDim.x * blockDim.x)
     { const uint64_t c = __ldg(&B[i].code), r = rc_code(c, K);
       s += mix64(c < r ? c : r);
+      s2 += mix64((c < r ? c : r) ^ 0x9e3779b97f4a7c15ull);
       if (bitmap != nullptr)
         { const uint32_t hc = hash_of(c), hr = hash_of(r);
           atomicOr(&bitmap[word_of(hc, hshift)], (unsigned long long) bits_of(hc));
           atomicOr(&bitmap[word_of(hr, hshift)], (unsigned long long) bits_of(hr));
         }
     }
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0 && s) atomicAdd(sig, s);
+  for (int o = 16; o > 0; o >>= 1)
+    { s += __shfl_down_sync(0xffffffffu, s, o); s2 += __shfl_down_sync(0xffffffffu, s2, o); }
+  if ((threadIdx.x & 31) == 0)
+    { if (s) atomicAdd(sig, s);
+      if (s2) atomicAdd(sig + 1, s2);
+    }
 }
 
 __device__ __forceinline__ uint64_t fx_ld(const uint64_t *p)
@@ -104,7 +109,7 @@ k_tile_reads(const int64_t *__restrict__ boff, int nreads, int64_t ntiles, int32
     { int mid = (lo + hi + 1) >> 1;
       if (boff[mid] <= t0) lo = mid; else hi = mid - 1;
     }
-  int l2 = lo, h2 = nreads;
+  int l2 = lo, h2 = nreads - 1;                         // the last READ starting before the tile's end
   while (l2 < h2)
     { int mid = (l2 + h2 + 1) >> 1;
       if (boff[mid] < t0 + FX_TILE) l2 = mid; else h2 = mid - 1;
@@ -357,6 +362,9 @@ KmerIndex *sort_kmers_deferred(const DeviceBlock *blk, int K, int suppress, cuda
     return sort_kmers(blk, K, suppress, stream);
   if (kmers64 > 0x7fffffffll)                          // `int kmers`, map.c:663,676
     fatal("Sort_Kmers: block holds %lld k-mers, more than 2^31-1", (long long) kmers64);
+  if (kmers64 >= (1ll << 30))                          // look-back words of the radix pass are 32 bits wide
+    fatal("Sort_Kmers: block holds %lld k-mers; this build sorts at most 2^30-1 per block: split the "
+          "database into smaller blocks (DBsplit -s)", (long long) kmers64);
   for (int i = 0; i < blk->nreads; i++)
     if (blk->h_rlen[i] < K)                            // damapper.c:403-410
       fatal("Sort_Kmers: block contains reads < %dbp long", K);
@@ -469,19 +477,29 @@ const KmerIndex *reads_view(const KmerIndex *ca, const KmerIndex *b, cudaStream_
       return a;
     }
   const int K = a->K;
-  // signature of the reference list (orientation-invariant)
-  unsigned long long *sig = dalloc<unsigned long long>(2);
-  unsigned long long hsig = 0;
   int grid = (b->len + 255) / 256;
   if (grid > sm_count() * 8) grid = sm_count() * 8;
-  CUDA_CHECK(cudaMemsetAsync(sig, 0, sizeof(unsigned long long) * 2, stream));
-  LAUNCH(k_ref_bitmap, grid, 256, 0, stream, b->list, b->len, K, 0, (unsigned long long *) nullptr, sig);
-  CUDA_CHECK(cudaMemcpyAsync(&hsig, sig, sizeof(hsig), cudaMemcpyDeviceToHost, stream));
-  CUDA_CHECK(cudaStreamSynchronize(stream));
-  if (a->filt != nullptr && a->filt_sig == hsig && a->filt_blen == b->len)
-    { dfree(sig);
-      g_filter_times[0] = g_filter_times[1] = g_filter_times[2] = 0.f;
-      return a->filt;
+  if (a->filt != nullptr)
+    { bool same = (b->src_uid != 0 && a->filt_uid == b->src_uid);      // the same block, either strand
+      if (!same && a->filt_blen == b->len)                             // another object: compare the hashes
+        { unsigned long long *sig = dalloc<unsigned long long>(2);
+          unsigned long long h[2] = { 0, 0 };
+          CUDA_CHECK(cudaMemsetAsync(sig, 0, sizeof(unsigned long long) * 2, stream));
+          LAUNCH(k_ref_bitmap, grid, 256, 0, stream, b->list, b->len, K, 0, (unsigned long long *) nullptr, sig);
+          CUDA_CHECK(cudaMemcpyAsync(h, sig, sizeof(h), cudaMemcpyDeviceToHost, stream));
+          if (!a->filt_sig_known)
+            CUDA_CHECK(cudaMemcpyAsync(a->filt_sig, a->filt_dsig, sizeof(a->filt_sig), cudaMemcpyDeviceToHost, stream));
+          CUDA_CHECK(cudaStreamSynchronize(stream));
+          a->filt_sig_known = true;
+          dfree(sig);
+          same = (h[0] == a->filt_sig[0] && h[1] == a->filt_sig[1]);
+          if (same && b->src_uid != 0)
+            a->filt_uid = b->src_uid;                                  // next time without the pass
+        }
+      if (same)
+        { g_filter_times[0] = g_filter_times[1] = g_filter_times[2] = 0.f;
+          return a->filt;
+        }
     }
   // bitmap: ~32 bits per reference k-mer (four bits set per k-mer: two per orientation, 12 % of the
   // bits at most).  In automatic mode it has to stay resident in L2 (2^29 bits = 64 MB): a lookup that
@@ -499,8 +517,7 @@ const KmerIndex *reads_view(const KmerIndex *ca, const KmerIndex *b, cudaStream_
   if (g_filter_mode == 1 &&
       (a->nfilt >= FILTER_MAX_BUILDS || 4.0 * b->len > 0.35 * (double) (1ll << lg) ||
        (double) b->len > 1.5 * (double) a->len))
-    { dfree(sig);
-      materialize_index(a, stream);
+    { materialize_index(a, stream);
       return a;
     }
   if (a->filt != nullptr)
@@ -516,7 +533,10 @@ const KmerIndex *reads_view(const KmerIndex *ca, const KmerIndex *b, cudaStream_
       cudaEventRecord(e0, stream);
     }
   CUDA_CHECK(cudaMemsetAsync(bitmap, 0, words * sizeof(unsigned long long), stream));
-  LAUNCH(k_ref_bitmap, grid, 256, 0, stream, b->list, b->len, K, wshift, bitmap, sig + 1);
+  if (a->filt_dsig == nullptr)
+    a->filt_dsig = dalloc<unsigned long long>(2);
+  CUDA_CHECK(cudaMemsetAsync(a->filt_dsig, 0, sizeof(unsigned long long) * 2, stream));
+  LAUNCH(k_ref_bitmap, grid, 256, 0, stream, b->list, b->len, K, wshift, bitmap, a->filt_dsig);
   if (g_time_kernels) cudaEventRecord(e1, stream);
   KmerIndex *f = build_filtered(a, b, bitmap, wshift, stream);
   if (g_time_kernels)
@@ -526,9 +546,10 @@ const KmerIndex *reads_view(const KmerIndex *ca, const KmerIndex *b, cudaStream_
       g_filter_times[1] = f->ms_extract; g_filter_times[2] = f->ms_sort;
     }
   g_filter_times[3] = (float) f->len;
-  dfree(bitmap); dfree(sig);
+  dfree(bitmap);
   a->filt = f;
-  a->filt_sig = hsig;
+  a->filt_uid = b->src_uid;
+  a->filt_sig_known = false;
   a->filt_blen = b->len;
   a->nfilt += 1;
   return f;

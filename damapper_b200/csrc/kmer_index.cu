@@ -241,7 +241,9 @@ __global__ void __launch_bounds__(256) k_compact(const KmerPos *__restrict__ src
 DeviceBlock *upload_block(const uint8_t *bases, const int64_t *boff, const int32_t *rlen,
                           int nreads, int tfirst, int maxlen, int64_t totlen, int64_t sizeof_db,
                           cudaStream_t stream)
-{ DeviceBlock *blk = new DeviceBlock();
+{ static uint64_t next_uid = 0;
+  DeviceBlock *blk = new DeviceBlock();
+  blk->uid = ++next_uid;
   blk->nreads = nreads; blk->tfirst = tfirst; blk->maxlen = maxlen; blk->totlen = totlen;
   blk->sizeof_db = sizeof_db;
   blk->total = boff[nreads];
@@ -294,7 +296,9 @@ k_unpack_bps(const uint8_t *__restrict__ packed, const int64_t *__restrict__ pof
 DeviceBlock *upload_block_packed(const uint8_t *packed, const int64_t *poff, int64_t packed_bytes,
                                  const int64_t *boff, const int32_t *rlen, int nreads, int tfirst,
                                  int maxlen, int64_t totlen, int64_t sizeof_db, cudaStream_t stream)
-{ DeviceBlock *blk = new DeviceBlock();
+{ static uint64_t next_uid = 1ull << 40;
+  DeviceBlock *blk = new DeviceBlock();
+  blk->uid = ++next_uid;
   blk->nreads = nreads; blk->tfirst = tfirst; blk->maxlen = maxlen; blk->totlen = totlen;
   blk->sizeof_db = sizeof_db;
   blk->total = boff[nreads];
@@ -444,11 +448,15 @@ KmerIndex *sort_kmers(const DeviceBlock *blk, int K, int suppress, cudaStream_t 
 { const int     nreads = blk->nreads;
   const int64_t kmers64 = blk->total - (int64_t) K * nreads;
   KmerIndex    *idx = new KmerIndex();
+  idx->src_uid = blk->uid;
 
   if (kmers64 <= 0)
     return idx;
   if (kmers64 > 0x7fffffffll)                          // `int kmers`, map.c:663,676
     fatal("Sort_Kmers: block holds %lld k-mers, more than 2^31-1", (long long) kmers64);
+  if (kmers64 >= (1ll << 30))                          // look-back words of the radix pass are 32 bits wide
+    fatal("Sort_Kmers: block holds %lld k-mers; this build sorts at most 2^30-1 per block: split the "
+          "database into smaller blocks (DBsplit -s)", (long long) kmers64);
   for (int i = 0; i < nreads; i++)
     if (blk->h_rlen[i] < K)                            // damapper.c:403-410
       fatal("Sort_Kmers: block contains reads < %dbp long", K);
@@ -536,6 +544,7 @@ void free_index(KmerIndex *idx)
 { if (idx == nullptr) return;
   dfree(idx->list);
   dfree(idx->lut);
+  dfree(idx->filt_dsig);
   free_index(idx->filt);
   free_block(idx->block);
   delete idx;

@@ -437,6 +437,10 @@ int main(int argc, char *argv[])
   builtin_sort = (getenv("DAMGPU_BUILTIN_SORT") != NULL || !on_path("LAsort"));
   if (builtin_sort && VERBOSE)
     printf("\n  LAsort is not on PATH (or DAMGPU_BUILTIN_SORT is set): built-in sort and merge of the .las files\n");
+  else if (builtin_sort && RANK == 0 && getenv("DAMGPU_BUILTIN_SORT") == NULL)
+    fprintf(stderr,"%s: LAsort is not on PATH: the .las files are sorted and merged by the built-in stand-in\n"
+                   "%*s  (its order follows DALIGNER's documented -a key and is not pinned against LAsort/LAmerge)\n",
+                   Prog_Name,(int) strlen(Prog_Name),"");
   for (i = 2+RANK; i < argc; i += NGPUS)                  /* damapper.c:825-914 */
     { char *broot, *aroot = refdb.root, name[4096], command[16384];
       damgpu_block  bview, aview;
