@@ -200,6 +200,19 @@ class DeviceBlock:
         else:
             self.h = init().damgpu_block_upload(C.byref(hb.c))
 
+    @classmethod
+    def from_host(cls, hb: HostBlock):
+        """Upload through the block view itself: 2 bits per base when the block carries its .bps image
+        (HostBlock.attach_packed), one byte per base otherwise."""
+        self = cls.__new__(cls)
+        self.host = hb
+        if getattr(hb, "packed", None) is not None:
+            self.h = init().damgpu_block_upload_packed(C.byref(hb.c), hb.packed.ctypes.data, hb.poff.ctypes.data,
+                                                       int(hb.packed.size))
+        else:
+            self.h = init().damgpu_block_upload(C.byref(hb.c))
+        return self
+
     def complement(self):
         load().damgpu_block_complement(self.h)
 

@@ -8,7 +8,7 @@ from damapper_b200 import api, dazzdb
 L = api.init(0)
 contigs, rb, rl, freq = bench.make_workload(seed=7)
 rd = dazzdb.load_block((rb, rl)); rf = dazzdb.load_block(contigs); rc = dazzdb.load_block(dazzdb.revcomp_contigs(contigs))
-hr, hg, hc = (bench.pinned_block(api, x, torch) for x in (rd, rf, rc))
+hr = bench.pinned_block(api, rd, torch, packed=True); hg, hc = bench.pinned_block(api, rf, torch), bench.pinned_block(api, rc, torch)
 api.set_filter_params(20, 0, 4)
 tmp = tempfile.mkdtemp(prefix="e2e_")
 api.set_options(mem_limit=64 << 30, sort_path=tmp)
