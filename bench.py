@@ -72,6 +72,8 @@ class ClockSampler(threading.Thread):
         self.samples = []
 
     def run(self):
+        if os.environ.get("BENCH_NO_SMI"):
+            return
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -262,7 +264,7 @@ def run_c4(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = api.init(local)
-    G, NB = 250_000_000, 8
+    G, NB = 250_000_000, int(os.environ.get("C4_NB", "8"))
     per_block = max(8, int(25000 * args.c4_scale))
     genome = synth.make_genome(G, seed=11)
     cuts = np.array([int(G * i / 8) for i in range(9)])
@@ -282,12 +284,14 @@ def run_c4(args):
     nrec = [0]
 
     def job():
+        tj = time.perf_counter()
         dg = api.DeviceBlock(hg)
         igf = api.Index(dg)
         dg.complement()
         igr = api.Index(dg)                       # dg stays complemented: only its sizes are used by the matches
         dw = api.DeviceBlock(hg)                  # the whole reference the Reporter aligns against
         nrec[0] = 0
+        torch.cuda.synchronize(); tb = [time.perf_counter()]
         for hb in blocks:
             dr = api.DeviceBlock.from_host(hb)             # 2 bits per base cross PCIe
             ir = api.Index(dr, deferred=True)
@@ -298,7 +302,11 @@ def run_c4(args):
             nrec[0] += rep.records(0)
             _ = rep.a                             # the record stream comes back to the host
             rep.free(); m.free(); ir.free(); dr.free()
+            tb.append(time.perf_counter())
         igf.free(); igr.free(); dg.free(); dw.free()
+        if os.environ.get("C4_TIMES"):
+            print("[c4] rank %d: setup %.1f ms, blocks %s ms" % (rank, (tb[0] - tj) * 1e3,
+                  " ".join("%.1f" % ((b - a) * 1e3) for a, b in zip(tb[:-1], tb[1:]))), file=sys.stderr, flush=True)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -310,23 +318,28 @@ def run_c4(args):
     sampler = ClockSampler(local)
     sync_all(); sampler.start()
     l0 = L.damgpu_launch_count()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
+    per_step = []
+    for _ in range(args.steps):                          # every job bracketed by a barrier + synchronize
+        t0 = time.perf_counter()
         job()
-    sync_all()
-    step_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        sync_all()
+        per_step.append((time.perf_counter() - t0) * 1e3)
     launches = L.damgpu_launch_count() - l0
     sampler.stop_flag.set(); sampler.join()
-    tot = torch.tensor([float(bases), float(nrec[0]), step_ms], dtype=torch.float64, device="cuda")
+    ps = torch.tensor(per_step, dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(bases), float(nrec[0])], dtype=torch.float64, device="cuda")
     if world > 1:
-        mx = tot.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ps, op=dist.ReduceOp.MAX)        # a job ends when its slowest rank ends
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        step_ms = float(mx[2].item())
+    per_step = [float(x) for x in ps.tolist()]
+    step_ms = float(np.mean(per_step))
     total_bases, total_rec = float(tot[0].item()), int(tot[1].item())
     if rank == 0:
         val = total_bases / (step_ms / 1e3)
         out = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64",
+               "ms_per_step": step_ms, "ms_per_step_median": float(np.median(per_step)), "ms_per_step_min": float(min(per_step)),
+               "ms_steps": per_step, "value_median": total_bases / (float(np.median(per_step)) / 1e3),
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64",
                "data": "synthetic",
                "config": {"workload": "C4: synthetic 250 Mbp reference (8 contigs, one block) + %d simulated 10 kbp reads at 15%% error in "
                                       "8 reads blocks, blocks round robin over the GPUs, k=20" % (NB * per_block),

@@ -925,10 +925,21 @@ void launch_align_duo(const AlignArgs &A, int njobs, cudaStream_t stream)
       per_sm = a < b ? a : b;
       if (per_sm < 1) per_sm = 1;
     }
+  // Slots (halves) are persistent and pull jobs from a counter.  With J jobs over S slots every slot runs
+  // ceil(J/S) or one job fewer; a half without a job still rides along with its warp's instruction
+  // stream, so the grid is shrunk to the smallest one with the same number of job rounds: every slot busy
+  // to the end, fewer warps sharing the issue slots (DAMGPU_DUO_FULLGRID=1: always the largest grid).
   const int per_block = DUO_WARPS * 2;
-  int nblocks = (njobs + per_block - 1) / per_block;
   const int cap = sm_count() * per_sm;
-  if (nblocks > cap) nblocks = cap;
+  int nblocks = (njobs + per_block - 1) / per_block;
+  if (nblocks > cap)
+    { static const bool full = (getenv("DAMGPU_DUO_FULLGRID") != nullptr);
+      const long long cap_slots = (long long) cap * per_block;
+      const long long rounds = (njobs + cap_slots - 1) / cap_slots;
+      const long long slots = (njobs + rounds - 1) / rounds;
+      nblocks = full ? cap : (int) ((slots + per_block - 1) / per_block);
+      if (nblocks > cap) nblocks = cap;
+    }
   if (dob) LAUNCH(k_align_duo<true>, nblocks, DUO_WARPS * 32, smem, stream, A);
   else     LAUNCH(k_align_duo<false>, nblocks, DUO_WARPS * 32, smem, stream, A);
 #ifdef DUO_DEBUG_DIV
