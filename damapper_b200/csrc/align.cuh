@@ -16,7 +16,7 @@ constexpr int ALIGN_W     = ALIGN_W_V;    // diagonal window in shared memory
 constexpr int ALIGN_W_BIG = 8192;         // diagonal window of the overflow kernel (global memory)
 #define ALIGN_STATE_BYTES(W) ((size_t) (W) * (2 * 8 + 10 * 4))
 constexpr int DUO_WARPS   = 4;            // duo kernel: warps per CTA (two jobs each)
-constexpr int DUO_W       = 32;           // duo kernel: diagonal window of a half in wide mode
+constexpr int DUO_W       = 64;           // duo kernel: diagonal window of a half in wide mode (global memory)
 #define LANE_ARENA(tps) (16 * (tps) + 512)   // duo kernel: Pebble cells per job, tps = read length / spacing
 
 // What the waves need of _Align_Spec (align.c:183-191); tables built on the host (align.c:207-269)
@@ -77,6 +77,7 @@ struct AlignArgs
   int             *nfailed;
   unsigned long long *stats;              // nalign, nwaves, ncells, empty-band events
   // duo kernel
+  int             *duo_win;               // wide-band windows, one per half-warp slot (duo_window_bytes)
   void            *lane_cells;            // Pebble arena: per job 8*(rlen/spacing)+256 cells
   const long long *lane_cell_base;        // per read: arena index of its first job
   const int64_t   *lane_job_off;          // per read: index of its first job
@@ -86,6 +87,8 @@ struct AlignArgs
 
 void launch_align(const AlignArgs &A, bool big, int nblocks, cudaStream_t stream);
 void launch_align_duo(const AlignArgs &A, int njobs, cudaStream_t stream);
+size_t duo_window_bytes(int nblocks);
+int  duo_max_blocks();
 void launch_unwind(const AlignArgs &A, int max_alns, cudaStream_t stream);
 
 }  // namespace damgpu

@@ -22,8 +22,10 @@
 //    besty) are captured in the registers of the lane that produced them; only the lane number is
 //    kept per half, and the values are fetched once when the wave call ends.
 //  * 1 % of the waves are wider than 16 diagonals (59 % of the calls meet one): the half then
-//    spills its diagonals to a 32-slot shared-memory window, runs those waves 16 diagonals at a
-//    time from there and returns to registers when the band has shrunk.  Bands over 32 diagonals
+//    spills its diagonals to a 64-slot window in global memory, runs those waves 16 diagonals at a
+//    time from there and returns to registers when the band has shrunk.  Bands over 64 diagonals
+//    (chimeric junctions, 30 %-error stretches: the band grows by two diagonals per wave until the wave
+//    dies; a 256-slot window kept them here and was slower than the hand-off: 4.3 against 3.7 ms on C5)
 //    fail the job, which is re-run by the warp kernel of align.cu (host loop in report.cu).
 //  * everything that happens once per wave call or per job (job fetch, seed walk, wave 0,
 //    Local_Alignment's F/R/re-run logic, record output) is a small scalar state machine run by
@@ -52,7 +54,7 @@ enum { PH_IDLE = 0, PH_SEED, PH_SEEDGO, PH_START, PH_WAVE, PH_ENDCALL, PH_FINISH
 
 struct __align__(16) LPebble { int ptr, diag, diff, mark; };         // align.c:344-349
 
-// window fields (shared memory, wide mode): inherited state is double-buffered
+// window fields (wide mode, global memory): inherited state is double-buffered
 enum { F_V = 0, F_TL, F_TH, F_HA, F_HB, F_MA, F_MB, F_INH };
 constexpr int DUO_WIN_WORDS = (2 * F_INH + 2) * DUO_W;
 
@@ -390,8 +392,9 @@ k_align_duo(const __grid_constant__ AlignArgs A)
   const unsigned dupsel = half ? 0x3232u : 0x1010u;       // PRMT selector: own ballot half, twice
   const bool lead = (hl == 0);
   DuoCtl &C = reinterpret_cast<DuoCtl *>(dsm)[wib * 2 + half];
-  int *const win = reinterpret_cast<int *>(dsm + sizeof(DuoCtl) * 2 * DUO_WARPS)
-                   + (size_t) (wib * 2 + half) * DUO_WIN_WORDS;
+  // the wide-band window of this slot: global memory (L1/L2-resident while in use; 1 % of the waves on plain
+  // reads, more on chimeric / low-quality ones where it saves re-running the job in the warp kernel)
+  int *const win = A.duo_win + ((size_t) (blockIdx.x * DUO_WARPS + wib) * 2 + half) * DUO_WIN_WORDS;
 #define WF(f, b, k) win[((f) * 2 + (b)) * DUO_W + ((k) & (DUO_W - 1))]
 #define WNA(k)      win[(2 * F_INH) * DUO_W + ((k) & (DUO_W - 1))]
 #define WNB(k)      win[(2 * F_INH + 1) * DUO_W + ((k) & (DUO_W - 1))]
@@ -542,7 +545,7 @@ k_align_duo(const __grid_constant__ AlignArgs A)
               }
           }
 
-          // ---- wide wave: 17..32 diagonals, state in the window, 16 at a time
+          // ---- wide wave: 17..64 diagonals, state in the window, 16 at a time
           const bool wid = go && wide;
           if (__any_sync(FULL, wid))
             { DBG_EV(8);
@@ -556,7 +559,8 @@ k_align_duo(const __grid_constant__ AlignArgs A)
                 }
               __syncwarp();
               int aclip = IMAX, bclip = -IMAX, rm = besta;
-              for (int ch = 0; ch < 2; ch++)
+              const int nch = (max(width, __shfl_xor_sync(FULL, width, 16)) + 15) >> 4;   // warp-uniform
+              for (int ch = 0; ch < nch; ch++)
                 { const int r = ch * 16 + hl, k = kh - r;  // ballot bit i of a half <-> r = ch*16 + i
                   const bool act = wid && (r < width);
                   int c = NEG, y = 0, hit = 0, ha = 0, hb = 0, ma = 0, mb = 0, na = 0, nb = 0;
@@ -692,18 +696,20 @@ k_align_duo(const __grid_constant__ AlignArgs A)
               __syncwarp();
               // trim the band (align.c:877-885 / 1531-1539)
               { const int n = besta - WAVE_LAG;
-                unsigned g0, g1;
-                { const int k = kh - hl;
-                  g0 = MY16(__ballot_sync(FULL, wid && hl < width && k >= low && k <= hgh && WF(F_V, cur, k) >= n));
-                }
-                { const int k = kh - 16 - hl;
-                  g1 = MY16(__ballot_sync(FULL, wid && 16 + hl < width && k >= low && k <= hgh && WF(F_V, cur, k) >= n));
-                }
-                const unsigned g = g0 | (g1 << 16);
+                int first = -1, last = -1;                // scan indices of the first / last diagonal kept
+                for (int ch = 0; ch < nch; ch++)
+                  { const int r = ch * 16 + hl, k = kh - r;
+                    const unsigned g = MY16(__ballot_sync(FULL, wid && r < width && k >= low && k <= hgh
+                                                                && WF(F_V, cur, k) >= n));
+                    if (g)
+                      { if (first < 0) first = ch * 16 + __ffs(g) - 1;
+                        last = ch * 16 + 31 - __clz(g);
+                      }
+                  }
                 if (wid)
-                  { if (g)
-                      { hgh = kh - (__ffs(g) - 1);
-                        low = kh - (31 - __clz(g));
+                  { if (first >= 0)
+                      { hgh = kh - first;
+                        low = kh - last;
                       }
                     else
                       hgh = low - 1;
@@ -909,7 +915,14 @@ k_align_duo(const __grid_constant__ AlignArgs A)
 }
 
 size_t duo_smem_bytes()
-{ return (size_t) DUO_WARPS * 2 * (sizeof(DuoCtl) + DUO_WIN_WORDS * sizeof(int)); }
+{ return (size_t) DUO_WARPS * 2 * sizeof(DuoCtl); }
+
+// bytes of wide-band windows for a grid of up to `nblocks` CTAs (AlignArgs.duo_win)
+size_t duo_window_bytes(int nblocks)
+{ return (size_t) nblocks * DUO_WARPS * 2 * DUO_WIN_WORDS * sizeof(int); }
+
+int duo_max_blocks()
+{ return sm_count() * 8; }
 
 // persistent half-warp slots: as many CTAs as fit on every SM, jobs from a counter
 void launch_align_duo(const AlignArgs &A, int njobs, cudaStream_t stream)
@@ -925,21 +938,13 @@ void launch_align_duo(const AlignArgs &A, int njobs, cudaStream_t stream)
       per_sm = a < b ? a : b;
       if (per_sm < 1) per_sm = 1;
     }
-  // Slots (halves) are persistent and pull jobs from a counter.  With J jobs over S slots every slot runs
-  // ceil(J/S) or one job fewer; a half without a job still rides along with its warp's instruction
-  // stream, so the grid is shrunk to the smallest one with the same number of job rounds: every slot busy
-  // to the end, fewer warps sharing the issue slots (DAMGPU_DUO_FULLGRID=1: always the largest grid).
+  // persistent slots (halves) pull jobs from a counter; the largest resident grid is the fastest (a grid
+  // shrunk to whole job rounds -- every slot busy to the end -- was 12 % slower: fewer warps hide less latency)
   const int per_block = DUO_WARPS * 2;
   const int cap = sm_count() * per_sm;
   int nblocks = (njobs + per_block - 1) / per_block;
-  if (nblocks > cap)
-    { static const bool full = (getenv("DAMGPU_DUO_FULLGRID") != nullptr);
-      const long long cap_slots = (long long) cap * per_block;
-      const long long rounds = (njobs + cap_slots - 1) / cap_slots;
-      const long long slots = (njobs + rounds - 1) / rounds;
-      nblocks = full ? cap : (int) ((slots + per_block - 1) / per_block);
-      if (nblocks > cap) nblocks = cap;
-    }
+  if (nblocks > cap) nblocks = cap;
+  if (nblocks > duo_max_blocks()) nblocks = duo_max_blocks();
   if (dob) LAUNCH(k_align_duo<true>, nblocks, DUO_WARPS * 32, smem, stream, A);
   else     LAUNCH(k_align_duo<false>, nblocks, DUO_WARPS * 32, smem, stream, A);
 #ifdef DUO_DEBUG_DIV

@@ -797,6 +797,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   long long  *d_cell_base = h2d(cell_base);
   void       *d_lane_cells = dalloc<unsigned char>((size_t) ncell * 16 + 16);
   LaneUnwind *d_unwind = dalloc<LaneUnwind>((size_t) aln_cap);
+  int        *d_duo_win = dalloc<int>(duo_window_bytes(std::min((njobs + 7) / 8 + 1, duo_max_blocks())) / sizeof(int) + 1);
   CUDA_CHECK(cudaMemsetAsync(d_unwind, 0xff, sizeof(LaneUnwind) * (size_t) aln_cap, stream));
 
   AlignArgs A;
@@ -814,7 +815,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   A.traces = d_traces; A.trace_top = d_ull; A.trace_cap = trace_cap;
   A.nfailed = d_ctr + 2; A.stats = d_ull + 1;
   A.lane_cells = d_lane_cells; A.lane_cell_base = d_cell_base; A.lane_job_off = d_job_off;
-  A.unwind = d_unwind; A.lane_tscratch = nullptr;
+  A.unwind = d_unwind; A.lane_tscratch = nullptr; A.duo_win = d_duo_win;
 
   TRACE("report: alloc");
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -991,7 +992,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   dfree(d_novl); dfree(d_asum); dfree(d_bsum); dfree(d_sz); dfree(d_tot);
   dfree(d_alns); dfree(d_traces); dfree(d_list); dfree(d_big);
   dfree(d_cells); dfree(d_tscr); dfree(d_ctr); dfree(d_ull);
-  dfree(d_cell_base); dfree(d_lane_cells); dfree(d_unwind);
+  dfree(d_cell_base); dfree(d_lane_cells); dfree(d_unwind); dfree(d_duo_win);
   dfree(d_jobs); dfree(d_job_off); dfree(d_cnt); dfree(rc.raw); dfree(d_tables);
   dfree(pk_a); dfree(pk_ac); dfree(pk_b);
   TRACE("report: frees");

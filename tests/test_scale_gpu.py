@@ -58,7 +58,13 @@ def test_c3_tenth_scale_repeat_rich(api, tmp_path):
     assert got["limit"] < 10000, "the hit cap did not engage: %r" % (got.get("limit"),)
     assert got["a"] == want[0], "M records differ"
     assert got["b"] == want[1], "R records differ"
-    assert got["prof"] == want[2], "-p track differs"
+    if got["prof"] != want[2]:
+        # The UNMODIFIED reference is not deterministic in its -p track on repeat-rich input when it runs
+        # threaded (seen: one run in six differs, once as a track of all 40s, with identical .las records;
+        # tests/test_cli_gpu.py has the same note).  Its single-threaded run is the authority then.
+        again = _ref_streams(wd, ("-M1", "-n.95", "-p", "-C"), 1)
+        assert again[0] == want[0] and again[1] == want[1]
+        assert got["prof"] == again[2], "-p track differs from the single-threaded reference as well"
     assert got["anrec"] > 5000
 
 
