@@ -50,7 +50,6 @@ SYMBOLS = {
     "damgpu_time_kernels": (None, [C.c_int]),
     "damgpu_set_align_tier": (None, [C.c_int, C.c_int]),
     "damgpu_radix_totals": (None, [C.POINTER(C.c_double), C.c_int]),
-    "damgpu_set_join_mode": (None, [C.c_int]),
     "damgpu_last_sort_times": (None, [C.POINTER(C.c_float)]),
     "damgpu_last_join_times": (None, [C.POINTER(C.c_float)]),
     "damgpu_Set_Filter_Params": (C.c_int, [C.c_int, C.c_int, C.c_int]),

@@ -194,8 +194,6 @@ int damgpu_init(int device)
   if (const char *t = getenv("DAMGPU_ALIGN"))
     g_align_tier = !strcmp(t, "warp") ? 0 : 1;
   g_chain_async = (getenv("DAMGPU_SYNC_CHAIN") == nullptr);
-  if (const char *t = getenv("DAMGPU_JOIN"))
-    g_join_mode = !strcmp(t, "merge") ? 1 : !strcmp(t, "lut") ? 0 : -1;
   if (const char *t = getenv("DAMGPU_RADIX"))
     g_radix_reload = !strcmp(t, "reload");
   g_radix_pf = g_sms;                                    // one tile per SM ahead (flat between 64 and 200 on B200)
@@ -234,7 +232,6 @@ void damgpu_set_align_tier(int tier, int slots)
 }
 void damgpu_last_join_times(float out[4]) { join_times(out); }
 void damgpu_radix_totals(double out[4], int reset) { radix_totals(out, reset); }
-void damgpu_set_join_mode(int mode) { g_join_mode = (mode == 0 || mode == 1) ? mode : -1; }
 void damgpu_last_sort_times(float out[3]) { out[0] = g_sort_times[0]; out[1] = g_sort_times[1]; out[2] = g_sort_times[2]; }
 
 int damgpu_Set_Filter_Params(int kmer, int suppress, int nthreads)   // map.c:124-150

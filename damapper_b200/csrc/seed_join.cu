@@ -9,7 +9,6 @@
 // derived `limit` from the run-product histogram, seeds are emitted at scanned offsets in
 // exactly the reference's emission order (code, a, b), so that the stable sort on the
 // reference's key bytes (apos, bread, aread) reproduces its array bit for bit.
-#include <string.h>
 #include "common.cuh"
 #include "index.cuh"
 #include "seeds.cuh"
@@ -144,181 +143,6 @@ k_join_match(const KmerPos *__restrict__ A, int alen, const KmerPos *__restrict_
     }
   const uint32_t local = add + x - nm;
 
-  if (tid == 0)
-    { uint64_t *st = tile_state + tile;
-      uint64_t excl = 0;
-      st_relaxed64(st, (tile == 0 ? J_INC : J_AGG) | total);
-      if (tile > 0)
-        { const uint64_t *p = st - 1;
-          while (true)
-            { uint64_t v = ld_relaxed64(p);
-              if (v & J_INC) { excl += v & J_VAL; break; }
-              if (v & J_AGG) { excl += v & J_VAL; p -= 1; continue; }
-              __nanosleep(20);
-            }
-          st_relaxed64(st, J_INC | (excl + total));
-        }
-      s_excl = excl;
-      if (last_tile)
-        *nruns_out = (uint32_t) (excl + total);
-    }
-  __syncthreads();
-  const uint64_t o = s_excl + local;
-  for (int j = 0; j < nm; j++)
-    *reinterpret_cast<int4 *>(runs + o + j) = *reinterpret_cast<int4 *>(&mine[j]);
-}
-
-// ---- the same join as a partitioned merge, for long lists ------------------------------------
-// Above a few million records the per-run lookups of k_join_match are random probes into a list
-// that no cache holds (C4: 250 M x 250 M records, 5 ms per call, a quarter of the HBM rate).  Here the
-// driver list is cut into tiles of MJ_TILE records; k_merge_partition finds, with two binary searches per
-// tile, the stretch of the target list that holds the codes of the tile (merge-path style: both lists
-// are sorted, so tile t's stretch follows tile t-1's); k_join_merge streams the tile and its stretch into
-// shared memory with coalesced 16-byte loads -- every record of either list is read once -- and each
-// thread merges its MJ_ITEMS consecutive driver records against the stretch there (one binary search, then
-// galloping forward).  Matching run pairs are compacted in code order exactly as k_join_match does it.
-// A stretch longer than MJ_BCAP records (skewed codes) is searched in global memory instead.
-constexpr int MJ_THREADS = 256;
-constexpr int MJ_ITEMS   = 8;
-constexpr int MJ_TILE    = MJ_THREADS * MJ_ITEMS;        // 2048 driver records
-constexpr int MJ_BCAP    = 3072;                         // target records staged per tile
-
-__global__ void __launch_bounds__(256)
-k_merge_partition(const KmerPos *__restrict__ D, int dlen, const KmerPos *__restrict__ T, int tlen,
-                  uint32_t ntiles, int2 *__restrict__ bounds)
-{ const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= ntiles) return;
-  const int64_t t0 = (int64_t) t * MJ_TILE;
-  const int64_t t1 = (t0 + MJ_TILE < dlen) ? t0 + MJ_TILE : dlen;
-  const uint64_t c0 = __ldg(&D[t0].code), c1 = __ldg(&D[t1 - 1].code);
-  int lo = 0, hi = tlen;
-  while (lo < hi)                                        // lower_bound(T, c0)
-    { const int mid = (int) (((int64_t) lo + hi) >> 1);
-      if (__ldg(&T[mid].code) < c0) lo = mid + 1; else hi = mid;
-    }
-  const int blo = lo;
-  hi = tlen;
-  while (lo < hi)                                        // upper_bound(T, c1), from blo on
-    { const int mid = (int) (((int64_t) lo + hi) >> 1);
-      if (__ldg(&T[mid].code) <= c1) lo = mid + 1; else hi = mid;
-    }
-  bounds[t] = make_int2(blo, lo);
-}
-
-__global__ void __launch_bounds__(MJ_THREADS)
-k_join_merge(const KmerPos *__restrict__ A, int alen, const KmerPos *__restrict__ B, int blen,
-             const int2 *__restrict__ bounds, int swap, Run *__restrict__ runs,
-             uint64_t *tile_state, uint32_t *tile_counter, uint32_t *nruns_out)
-{ __shared__ uint64_t s_a[MJ_TILE + 1];
-  __shared__ uint64_t s_b[MJ_BCAP];
-  __shared__ uint32_t s_tile, s_wsum[MJ_THREADS / 32];
-  __shared__ uint64_t s_excl;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0)
-    s_tile = atomicAdd(tile_counter, 1u);
-  __syncthreads();
-  const uint32_t tile = s_tile;
-  const int64_t  t0 = (int64_t) tile * MJ_TILE;
-  const int      na_t = (int) ((t0 + MJ_TILE < alen) ? MJ_TILE : alen - t0);
-  const bool last_tile = (t0 + MJ_TILE >= alen);
-  const int2 bd = bounds[tile];
-  const int  nb_t = bd.y - bd.x;
-  const bool staged = (nb_t <= MJ_BCAP);
-
-  const uint4 *A4 = reinterpret_cast<const uint4 *>(A + t0);
-  for (int i = tid; i < na_t; i += MJ_THREADS)
-    { const uint4 v = __ldg(A4 + i);
-      s_a[i + 1] = ((uint64_t) v.y << 32) | v.x;
-    }
-  if (tid == 0)
-    s_a[0] = (t0 > 0) ? __ldg(&A[t0 - 1].code) : ~__ldg(&A[0].code);   // a code that differs from A[0]'s
-  if (staged)
-    { const uint4 *B4 = reinterpret_cast<const uint4 *>(B + bd.x);
-      for (int i = tid; i < nb_t; i += MJ_THREADS)
-        { const uint4 v = __ldg(B4 + i);
-          s_b[i] = ((uint64_t) v.y << 32) | v.x;
-        }
-    }
-  __syncthreads();
-
-  // blocked arrangement: thread owns driver records t0 + tid*MJ_ITEMS + j, so run order = thread order
-  Run mine[MJ_ITEMS];
-  int nm = 0;
-  int pos = 0;                                           // merge position in the stretch (relative to bd.x)
-  bool first = true;
-#pragma unroll
-  for (int j = 0; j < MJ_ITEMS; j++)
-    { const int li = tid * MJ_ITEMS + j;
-      if (li >= na_t) break;
-      const uint64_t c = s_a[li + 1];
-      if (c == s_a[li]) continue;                        // not a run head
-      int lo;
-      if (staged)
-        { if (first)                                     // lower_bound in the staged stretch
-            { int l = 0, h = nb_t;
-              while (l < h)
-                { const int mid = (l + h) >> 1;
-                  if (s_b[mid] < c) l = mid + 1; else h = mid;
-                }
-              pos = l; first = false;
-            }
-          else                                           // gallop forward from the last position
-            { int step = 1, l = pos, h = pos;
-              while (h < nb_t && s_b[h] < c) { l = h + 1; h += step; step <<= 1; }
-              if (h > nb_t) h = nb_t;
-              while (l < h)
-                { const int mid = (l + h) >> 1;
-                  if (s_b[mid] < c) l = mid + 1; else h = mid;
-                }
-              pos = l;
-            }
-          if (pos >= nb_t || s_b[pos] != c) continue;
-          int e = pos + 1;
-          while (e < nb_t && s_b[e] == c) e++;
-          lo = bd.x + pos;
-          const int eb = bd.x + e;
-          // end of the driver run: inside the tile, else gallop in global memory
-          int ea = li + 1;
-          while (ea < na_t && s_a[ea + 1] == c) ea++;
-          int ae = (int) t0 + ea;
-          if (ea == na_t && !last_tile)
-            ae = run_end(A, ae - 1, alen, c);
-          const int ia = (int) t0 + li;
-          if (swap) { mine[nm].ia = lo; mine[nm].na = eb - lo; mine[nm].jb = ia; mine[nm].nb = ae - ia; }
-          else      { mine[nm].ia = ia; mine[nm].na = ae - ia; mine[nm].jb = lo; mine[nm].nb = eb - lo; }
-          nm++;
-        }
-      else                                               // long stretch: search it where it lies
-        { int l = bd.x, h = bd.y;
-          while (l < h)
-            { const int mid = (int) (((int64_t) l + h) >> 1);
-              if (B[mid].code < c) l = mid + 1; else h = mid;
-            }
-          if (l >= bd.y || B[l].code != c) continue;
-          lo = l;
-          const int eb = run_end(B, lo, blen, c);
-          const int ia = (int) t0 + li;
-          const int ae = run_end(A, ia, alen, c);
-          if (swap) { mine[nm].ia = lo; mine[nm].na = eb - lo; mine[nm].jb = ia; mine[nm].nb = ae - ia; }
-          else      { mine[nm].ia = ia; mine[nm].na = ae - ia; mine[nm].jb = lo; mine[nm].nb = eb - lo; }
-          nm++;
-        }
-    }
-
-  // block exclusive scan of nm, then the chained scan over the tiles (as k_join_match)
-  uint32_t x = nm;
-  for (int o = 1; o < 32; o <<= 1)
-    { uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
-    }
-  if (lane == 31) s_wsum[warp] = x;
-  __syncthreads();
-  uint32_t add = 0, total = 0;
-  for (int w = 0; w < MJ_THREADS / 32; w++)
-    { if (w < warp) add += s_wsum[w];
-      total += s_wsum[w];
-    }
-  const uint32_t local = add + x - nm;
   if (tid == 0)
     { uint64_t *st = tile_state + tile;
       uint64_t excl = 0;
@@ -494,7 +318,6 @@ static int compute_limit(const unsigned long long *histo, uint64_t mem_limit, in
   return j;
 }
 
-int   g_join_mode = -1;                                 // -1 by size, 0 prefix table, 1 partitioned merge
 float g_join_times[4] = { 0, 0, 0, 0 };                 // lut ms, match ms, alen, blen of the last call
 static cudaEvent_t g_join_ev[3] = { nullptr, nullptr, nullptr };
 
@@ -531,55 +354,40 @@ SeedSet *merge_join(const KmerIndex *aidx, const DeviceBlock *ablock, const Kmer
 
   TRACE(nullptr);
   // driver = shorter list; target = longer list, searched through a prefix table over the top P
-  // bits of the code (about 4 target records per bucket).  The table of a reads index is kept
-  // with the index: it serves both orientations and every reference block.
+  // bits of the code (about 4 target records per bucket), kept with the index it was built over.
   const bool swap = (blen < alen);
   const KmerPos *D = swap ? B : A, *T = swap ? A : B;
   const int dlen = swap ? blen : alen, tlen = swap ? alen : blen;
-  // long lists: partitioned merge (every record of both lists read once); short ones: prefix table +
-  // one lookup per driver run.  DAMGPU_JOIN=merge|lut overrides, DAMGPU_JOIN_MERGE_MIN sets the threshold.
-  static const long long jmin = getenv("DAMGPU_JOIN_MERGE_MIN") ? atoll(getenv("DAMGPU_JOIN_MERGE_MIN")) : (16ll << 20);
-  const bool use_merge = (g_join_mode >= 0) ? (g_join_mode == 1) : (dlen >= jmin);
+  int P = 1;
+  while ((1ll << P) * 4 < tlen && P < 26) P++;
+  if (P > 2 * K) P = 2 * K;
+  const int shift = 2 * K - P;
+  const uint32_t np = 1u << P;
+  uint32_t *lut;
   cudaEvent_t *ev = g_join_ev;                           // lut | match (bench: damgpu_last_join_times)
   if (g_time_kernels)
     { if (ev[0] == nullptr)
         for (int i = 0; i < 3; i++) cudaEventCreate(&ev[i]);
       cudaEventRecord(ev[0], stream);
     }
-  uint32_t *lut = nullptr;
-  int2 *bounds = nullptr;
-  int P = 1;
-  while ((1ll << P) * 4 < tlen && P < 26) P++;
-  if (P > 2 * K) P = 2 * K;
-  const int shift = 2 * K - P;
-  const uint32_t np = 1u << P;
-  const uint32_t ntiles = use_merge ? (uint32_t) (((int64_t) dlen + MJ_TILE - 1) / MJ_TILE)
-                                    : (uint32_t) (((int64_t) dlen + JM_TILE - 1) / JM_TILE);
-  if (use_merge)
-    { bounds = dalloc<int2>((size_t) ntiles + 1);
-      LAUNCH(k_merge_partition, (ntiles + 255) / 256, 256, 0, stream, D, dlen, T, tlen, ntiles, bounds);
-    }
-  else if (swap && aidx->lut != nullptr)
-    lut = aidx->lut;
+  const KmerIndex *tidx = swap ? aidx : bidx;          // the table stays with the list it indexes: a reads
+  if (tidx->lut != nullptr)                             // index serves both strands and every reference block,
+    lut = tidx->lut;                                    // a resident reference index every reads block
   else
     { lut = dalloc<uint32_t>((size_t) np + 2);
       LAUNCH(k_build_lut, (tlen + 256 * LUT_UNROLL) / (256 * LUT_UNROLL), 256, 0, stream, T, tlen, shift, np, lut);
-      if (swap)
-        aidx->lut = lut;
+      tidx->lut = lut;
     }
 
   if (g_time_kernels) cudaEventRecord(ev[1], stream);
+  const uint32_t ntiles = (uint32_t) (((int64_t) dlen + JM_TILE - 1) / JM_TILE);
   uint64_t *state = dalloc<uint64_t>((size_t) ntiles + 2);
   CUDA_CHECK(cudaMemsetAsync(state, 0, sizeof(uint64_t) * ((size_t) ntiles + 2), stream));
   uint32_t *counter = reinterpret_cast<uint32_t *>(state + ntiles);      // [0]=tile counter, [1]=nruns
   // worst case every driver record heads a matching run (normally a few percent do)
   Run *runs = dalloc<Run>((size_t) dlen + 1);
-  if (use_merge)
-    LAUNCH(k_join_merge, ntiles, MJ_THREADS, 0, stream, D, dlen, T, tlen, bounds, swap ? 1 : 0,
-           runs, state, counter, counter + 1);
-  else
-    LAUNCH(k_join_match, ntiles, JM_THREADS, 0, stream, D, dlen, T, tlen, lut, shift, swap ? 1 : 0,
-           runs, state, counter, counter + 1);
+  LAUNCH(k_join_match, ntiles, JM_THREADS, 0, stream, D, dlen, T, tlen, lut, shift, swap ? 1 : 0,
+         runs, state, counter, counter + 1);
   if (g_time_kernels)
     { cudaEventRecord(ev[2], stream);                    // read by join_times(), no sync here
       g_join_times[2] = (float) alen; g_join_times[3] = (float) blen;
@@ -598,8 +406,6 @@ SeedSet *merge_join(const KmerIndex *aidx, const DeviceBlock *ablock, const Kmer
   CUDA_CHECK(cudaMemcpyAsync(ss->histo.data(), gram, sizeof(unsigned long long) * (MAXGRAM + 1),
                              cudaMemcpyDeviceToHost, stream));
   CUDA_CHECK(cudaStreamSynchronize(stream));
-  if (!swap && lut != nullptr) dfree(lut);
-  dfree(bounds);
   dfree(state);
   dfree(gram);
 

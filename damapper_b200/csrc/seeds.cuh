@@ -17,7 +17,6 @@ struct SeedSet
 SeedSet *merge_join(const KmerIndex *aidx, const DeviceBlock *ablock, const KmerIndex *bidx,
                     const DeviceBlock *bblock, int K, uint64_t mem_limit, cudaStream_t stream);
 void     free_seeds(SeedSet *ss);
-extern int g_join_mode;           // -1 chosen by list length, 0 prefix table + lookups, 1 partitioned merge
 void     join_times(float out[4]);   // ms of the prefix table build and the match kernel of the last call
 
 }  // namespace damgpu

@@ -98,9 +98,6 @@ void damgpu_set_align_tier(int tier, int slots);
  * record and pass), [1]=ms of the passes (CUDA events on the launching stream), [2]=pass
  * launches, [3]=sorts */
 void damgpu_radix_totals(double out[4], int reset);
-/* merge-join kernel: -1 = by list length (default), 0 = prefix table + one lookup per run, 1 = partitioned
- * merge (seed_join.cu); same seeds either way */
-void damgpu_set_join_mode(int mode);
 /* ms of the last Sort_Kmers: [0]=extraction kernel, [1]=all radix passes, [2]=#passes */
 void damgpu_last_sort_times(float out[3]);
 /* of the last merge-join (with damgpu_time_kernels on): [0]=ms of the prefix table build (0 when the

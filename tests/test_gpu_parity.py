@@ -102,11 +102,8 @@ def test_alignment_tiers_give_the_same_records(api, oracle_mod, tier, slots, cfg
     ("C1", 0.1, 4, 20, 0), ("C3", 0.002, 5, 14, 0), ("C1", 0.05, 6, 16, 10),
     ("C5", 0.1, 7, 32, 0), ("C1", 0.05, 8, 12, 0), ("C1", 0.05, 9, 9, 3),
 ])
-@pytest.mark.parametrize("join_mode", [0, 1])
-def test_index_and_seeds_match_oracle(api, oracle_mod, cfg, scale, seed, kmer, suppress, join_mode):
-    """Sort_Kmers (a2-a5) and merge-join + seed sort (a6-a9) arrays, byte for byte, with both join kernels
-    (prefix table + lookups; partitioned merge, the form long lists take)."""
-    api.load().damgpu_set_join_mode(join_mode)
+def test_index_and_seeds_match_oracle(api, oracle_mod, cfg, scale, seed, kmer, suppress):
+    """Sort_Kmers (a2-a5) and merge-join + seed sort (a6-a9) arrays, byte for byte."""
     orc = oracle_mod
     contigs, rb, rl, rd, rf, rc = make_case(cfg, scale, seed)
     api.set_filter_params(kmer, suppress, 4)
@@ -131,7 +128,6 @@ def test_index_and_seeds_match_oracle(api, oracle_mod, cfg, scale, seed, kmer, s
     # complemented index too
     igc = api.Index(dg)
     assert igc.download().tobytes() == orc.sort_kmers(orc.HostBlock(*rc), kmer, suppress).tobytes()
-    api.load().damgpu_set_join_mode(-1)
 
 
 @pytest.mark.parametrize("cfg,scale,seed,kmer,bits", [
