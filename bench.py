@@ -271,7 +271,7 @@ def run_c4(args):
     contigs = [genome[cuts[i]:cuts[i + 1]] for i in range(8)]
     cnt = np.bincount(genome[:10_000_000], minlength=4).astype(np.float64)
     freq = tuple(float(x) for x in (cnt / cnt.sum()).astype(np.float32))
-    hg = pinned_block(api, dazzdb.load_block(contigs), torch, packed=False)
+    hg = pinned_block(api, dazzdb.load_block(contigs), torch, packed=True)
     mine = list(range(rank, NB, world))
     blocks, bases = [], 0
     for b in mine:
@@ -285,28 +285,43 @@ def run_c4(args):
 
     def job():
         tj = time.perf_counter()
-        dg = api.DeviceBlock(hg)
+        dg = api.DeviceBlock.from_host(hg)        # the reference too crosses PCIe at 2 bits per base
         igf = api.Index(dg)
         dg.complement()
         igr = api.Index(dg)                       # dg stays complemented: only its sizes are used by the matches
-        dw = api.DeviceBlock(hg)                  # the whole reference the Reporter aligns against
+        dw = api.DeviceBlock.from_host(hg)        # the whole reference the Reporter aligns against
         nrec[0] = 0
         torch.cuda.synchronize(); tb = [time.perf_counter()]
+        detail = os.environ.get("C4_TIMES") == "2"
         for hb in blocks:
+            tc = [time.perf_counter()]
             dr = api.DeviceBlock.from_host(hb)             # 2 bits per base cross PCIe
+            tc.append(time.perf_counter())
             ir = api.Index(dr, deferred=True)
             m = api.Mapper(dr, ir)
+            tc.append(time.perf_counter())
             m.match(dg, igf, 0, 1)
+            tc.append(time.perf_counter())
             m.match(dg, igr, 1, 0)
+            tc.append(time.perf_counter())
             rep = m.report(dw, 0.85, 100, freq, 1)
+            tc.append(time.perf_counter())
             nrec[0] += rep.records(0)
             _ = rep.a                             # the record stream comes back to the host
+            tc.append(time.perf_counter())
             rep.free(); m.free(); ir.free(); dr.free()
+            tc.append(time.perf_counter())
+            if detail:
+                print("[c4]   upload %.1f | index+mapper %.1f | match f %.1f | match r %.1f | report %.1f | bytes %.1f | free %.1f"
+                      % tuple((b - a) * 1e3 for a, b in zip(tc[:-1], tc[1:])), file=sys.stderr, flush=True)
             tb.append(time.perf_counter())
         igf.free(); igr.free(); dg.free(); dw.free()
         if os.environ.get("C4_TIMES"):
-            print("[c4] rank %d: setup %.1f ms, blocks %s ms" % (rank, (tb[0] - tj) * 1e3,
-                  " ".join("%.1f" % ((b - a) * 1e3) for a, b in zip(tb[:-1], tb[1:]))), file=sys.stderr, flush=True)
+            fr, to = C.c_uint64(0), C.c_uint64(0)
+            L.damgpu_device_memory(C.byref(fr), C.byref(to))
+            print("[c4] rank %d: setup %.1f ms, blocks %s ms; device memory not in use (free + cached) %.2f GB" % (
+                  rank, (tb[0] - tj) * 1e3, " ".join("%.1f" % ((b - a) * 1e3) for a, b in zip(tb[:-1], tb[1:])),
+                  fr.value / 1e9), file=sys.stderr, flush=True)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -347,7 +362,7 @@ def run_c4(args):
                           "l2": "inputs larger than L2: a reads block is 250 MB, the reference lists 4 GB per strand",
                           "index": "built locally by every rank, once per job"},
                "e2e": {"value": val, "unit": UNIT, "ms_per_step": step_ms,
-                       "h2d_bytes_per_step": int(sum(b.packed.size for b in blocks) + 2 * hg.bases.size),
+                       "h2d_bytes_per_step": int(sum(b.packed.size for b in blocks) + 2 * hg.packed.size),
                        "d2h_bytes_per_step": None},
                "records": total_rec, "gpu_launches": int(launches), "clocks": sampler.summary()}
         os.write(real_out, (json.dumps(out) + "\n").encode())

@@ -121,10 +121,18 @@ def load():
     return _lib
 
 
+_inited = None
+
+
 def init(device: int = -1):
+    """damgpu_init once per device (the library itself returns at once when it is set up already)."""
+    global _inited
     L = load()
+    if _inited is not None and (device < 0 or device == _inited):
+        return L
     if L.damgpu_init(device) != 0:
         raise RuntimeError("libdamgpu: no usable CUDA device: %s" % L.damgpu_last_error().decode())
+    _inited = device if device >= 0 else 0
     return L
 
 

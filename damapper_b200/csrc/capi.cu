@@ -169,7 +169,10 @@ using namespace damgpu;
 extern "C" {
 
 int damgpu_init(int device)
-{ int n = 0;
+{ static int ready_dev = -1;
+  if (g_ready && (device < 0 || device == ready_dev))    // already set up on this device: nothing to ask the driver
+    return 0;
+  int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0)
     { g_last_error = (e != cudaSuccess) ? cudaGetErrorString(e) : "no CUDA devices";
@@ -181,14 +184,16 @@ int damgpu_init(int device)
     }
   int dev = 0;
   cudaGetDevice(&dev);
-  cudaDeviceProp prop;
-  e = cudaGetDeviceProperties(&prop, dev);
+  int major = 0, sms = 0;                                // two attributes, not the whole property record
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) { g_last_error = cudaGetErrorString(e); return 1; }
-  if (prop.major != 10)
+  if (major != 10)
     { g_last_error = "device is not sm_100 (Blackwell B200)";
       return 1;
     }
-  g_sms = prop.multiProcessorCount;
+  g_sms = sms;
+  ready_dev = dev;
   g_trace = (getenv("DAMGPU_TRACE") != nullptr);
   g_debug_sync = (getenv("DAMGPU_DEBUG_SYNC") != nullptr);
   if (const char *t = getenv("DAMGPU_ALIGN"))
