@@ -179,7 +179,11 @@ k_extract_filtered(const uint8_t *__restrict__ bases, const int64_t *__restrict_
           // bases is 16-byte aligned and q a multiple of 16; the test is spelled out because the build
           // without it faulted on B200 ("misaligned address" at this load) although every address
           // checked on the device was aligned
+#ifdef FX_NO_ALIGN_GUARD                                    /* dev: reproduce the fault under compute-sanitizer */
+          if (q >= 0 && q + 16 <= total)
+#else
           if (q >= 0 && q + 16 <= total && (((uintptr_t) (bases + q)) & 15) == 0)
+#endif
             { uint4 v = __ldcs(reinterpret_cast<const uint4 *>(bases + q));
               uint32_t x[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
