@@ -88,3 +88,43 @@ def test_builtin_sort_errors_and_path_probe(post, tmp_path):
     assert post.las_sort_cat(str(tmp_path / "e.M").encode(), 1, str(tmp_path / "e.las").encode(), 1, 0) == 0
     assert open(tmp_path / "e.las", "rb").read() == struct.pack("<qi", 0, 100)
     assert post.on_path(b"sh") == 1 and post.on_path(b"no-such-program-xyz") == 0
+
+
+def test_builtin_merge_over_reads_blocks(post, tmp_path):
+    """The R family of several reads blocks (damapper.c:903-911 runs LAsort + LAmerge per reads block; merging
+    the per-block ref.reads.<b>.las files is one more LAmerge, as HPC.damapper's scripts do): two blocks'
+    worth of per-thread files are merged block by block, the two results merged again.  Nothing is lost, chains
+    stay whole, the -a key orders the final file, and merging an already merged file changes nothing."""
+    import shutil
+    from damapper_b200 import las
+    from oracle.make_golden import CASES
+    g = np.load(os.path.join(GOLDEN, "c5_cover_profile.npz"))
+    spacing = CASES["c5_cover_profile"][4].get("spacing", 100)
+    recs = las.stream_records(g["b"].tobytes(), spacing)
+    ch = _chains(recs)
+    assert len(ch) > 100
+    # two "reads blocks": chains dealt alternately (both hold every contig), each written as 4 per-thread files
+    blocks = [ch[0::2], ch[1::2]]
+    for b, part in enumerate(blocks, start=1):
+        for i in range(4):
+            sub = [r for c in part[len(part) * i // 4:len(part) * (i + 1) // 4] for r in c]
+            with open(tmp_path / ("ref.reads%d.R%d.las" % (b, i + 1)), "wb") as f:
+                f.write(struct.pack("<qi", len(sub), spacing))
+                for r in sub:
+                    f.write(_blob(r, 1))
+        out = str(tmp_path / ("blk.R%d.las" % b))
+        assert post.las_sort_cat(str(tmp_path / ("ref.reads%d.R" % b)).encode(), 4, out.encode(), 1, 0) == 0
+    final = str(tmp_path / "ref.reads.las")
+    assert post.las_sort_cat(str(tmp_path / "blk.R").encode(), 2, final.encode(), 1, 0) == 0
+    ts, got = las.read_las(final)
+    gch = _chains(got)
+    key = lambda c: tuple(_blob(r, 1) for r in c)
+    assert ts == spacing and len(got) == len(recs)
+    assert sorted(map(key, gch)) == sorted(map(key, ch))
+    heads = [(c[0]["aread"], c[0]["abpos"]) for c in gch]
+    assert heads == sorted(heads)
+    # idempotence: a merged file merged again is the same file
+    shutil.copy(final, tmp_path / "again.R1.las")
+    again = str(tmp_path / "again.las")
+    assert post.las_sort_cat(str(tmp_path / "again.R").encode(), 1, again.encode(), 1, 0) == 0
+    assert open(again, "rb").read() == open(final, "rb").read()
