@@ -176,9 +176,11 @@ k_extract_filtered(const uint8_t *__restrict__ bases, const int64_t *__restrict_
       for (int c = tid; c < (FX_TILE + 32) / 16; c += FX_THREADS)
         { int64_t q = t0 - 32 + (int64_t) c * 16;
           uint32_t w = 0;
-          // bases is 16-byte aligned and q a multiple of 16; the test is spelled out because the build
-          // without it faulted on B200 ("misaligned address" at this load) although every address
-          // checked on the device was aligned
+          // bases is 16-byte aligned and q a multiple of 16.  The alignment test is spelled out because a
+          // round-1 build without it faulted on B200 ("misaligned address" at this load).  Round 2 fixed an
+          // out-of-bounds read of boff in k_tile_reads / the s_boff staging (l2 could reach nreads); since
+          // then the build without the test (-DFX_NO_ALIGN_GUARD) runs the full-size C2 steps clean, so
+          // the test is belt and braces (compute-sanitizer is closed on this pool: no memcheck run)
 #ifdef FX_NO_ALIGN_GUARD                                    /* dev: reproduce the fault under compute-sanitizer */
           if (q >= 0 && q + 16 <= total)
 #else
