@@ -143,7 +143,10 @@ __device__ __forceinline__ uint64_t window_code(const uint64_t *s_pack, int off,
 // ranks inside a tile come from ballots (item-major, then warp, then lane = ascending q), the tile's
 // base from a chained scan over the tile totals (look-back by a whole warp, 32 predecessors per
 // round trip).  counters: [0] ticket, [1] survivors, [2] overflow.
-__global__ void __launch_bounds__(FX_THREADS, 4)
+#ifndef FX_MINB
+#define FX_MINB 4
+#endif
+__global__ void __launch_bounds__(FX_THREADS, FX_MINB)
 k_extract_filtered(const uint8_t *__restrict__ bases, const int64_t *__restrict__ boff, int nreads,
                    int64_t total, int K, const int32_t *__restrict__ tile_tab,
                    const unsigned long long *__restrict__ bitmap, int hshift, KmerPos *__restrict__ out,
@@ -412,7 +415,7 @@ static KmerIndex *build_filtered(const KmerIndex *a, const KmerIndex *b, unsigne
   uint32_t *hist = dalloc<uint32_t>(256 * 16);
   uint64_t *state = dalloc<uint64_t>((size_t) ntiles + 2);
   uint32_t *counters = reinterpret_cast<uint32_t *>(state + ntiles);      // 3 words used
-  int grid = sm_count() * 4;                           // resident CTAs (64 registers), tiles by ticket
+  int grid = sm_count() * FX_MINB;                     // resident CTAs, tiles by ticket
   if (grid > ntiles) grid = (int) ntiles;
 
   cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
