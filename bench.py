@@ -86,7 +86,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.05)
+            self.stop_flag.wait(0.2)                      # the recipe's -lms 200
 
     def summary(self):
         sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
@@ -331,7 +331,9 @@ def run_c4(args):
     for _ in range(max(1, min(args.warmup, 2))):
         job()
     sampler = ClockSampler(local)
-    sync_all(); sampler.start()
+    sync_all()
+    if rank == 0:
+        sampler.start()
     l0 = L.damgpu_launch_count()
     per_step = []
     for _ in range(args.steps):                          # every job bracketed by a barrier + synchronize
@@ -340,7 +342,9 @@ def run_c4(args):
         sync_all()
         per_step.append((time.perf_counter() - t0) * 1e3)
     launches = L.damgpu_launch_count() - l0
-    sampler.stop_flag.set(); sampler.join()
+    sampler.stop_flag.set()
+    if rank == 0:
+        sampler.join()
     ps = torch.tensor(per_step, dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(bases), float(nrec[0])], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -495,7 +499,8 @@ def main():
     L.damgpu_radix_totals(rtot, 1)                       # reset: the timed steps only
     sampler = ClockSampler(local)
     sync_all()
-    sampler.start()
+    if rank == 0:                                        # one poller per node: nvidia-smi takes driver locks
+        sampler.start()
     l0 = L.damgpu_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -553,7 +558,8 @@ def main():
         sync_all()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
         sampler.stop_flag.set()                          # clocks were sampled over both timed regions
-        sampler.join()
+        if rank == 0:
+            sampler.join()
     finally:
         sampler.stop_flag.set()
         shutil.rmtree(tmpdir, ignore_errors=True)
