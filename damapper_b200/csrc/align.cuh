@@ -82,7 +82,6 @@ struct AlignArgs
   const long long *lane_cell_base;        // per read: arena index of its first job
   const int64_t   *lane_job_off;          // per read: index of its first job
   LaneUnwind      *unwind;                // per alignment record (aln_cap)
-  uint16_t        *lane_tscratch;         // unused
 };
 
 void launch_align(const AlignArgs &A, bool big, int nblocks, cudaStream_t stream);

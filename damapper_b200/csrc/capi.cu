@@ -27,7 +27,7 @@ static float       g_sort_times[3] = { 0, 0, 0 };
 Params g_par;          // filter parameters + the map.h globals
 bool   g_trace = false;
 bool   g_debug_sync = false;
-int    g_align_tier = 1, g_align_slots = 2;
+int    g_align_tier = 1;
 bool   g_chain_async = true;
 
 void trace_mark(const char *name)

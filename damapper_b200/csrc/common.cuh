@@ -62,7 +62,7 @@ void trace_mark(const char *name);
 extern bool g_trace;
 // first tier of the alignment phase: 1 = two jobs per warp (align_duo.cu, default), 0 = warp per
 // job (align.cu, also the tier that re-runs what outgrows the first).  DAMGPU_ALIGN=warp|duo.
-extern int g_align_tier, g_align_slots;
+extern int g_align_tier;
 extern bool g_chain_async;         // chain kernel on its own stream (DAMGPU_SYNC_CHAIN=1 turns it off)
 
 // ---- radix_sort.cu -------------------------------------------------------------------

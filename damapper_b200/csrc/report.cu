@@ -815,7 +815,7 @@ ReportOut *reporter(Mapper *m, const DeviceBlock *ref, double ave_corr, const fl
   A.traces = d_traces; A.trace_top = d_ull; A.trace_cap = trace_cap;
   A.nfailed = d_ctr + 2; A.stats = d_ull + 1;
   A.lane_cells = d_lane_cells; A.lane_cell_base = d_cell_base; A.lane_job_off = d_job_off;
-  A.unwind = d_unwind; A.lane_tscratch = nullptr; A.duo_win = d_duo_win;
+  A.unwind = d_unwind; A.duo_win = d_duo_win;
 
   TRACE("report: alloc");
   cudaEvent_t e0 = nullptr, e1 = nullptr;
