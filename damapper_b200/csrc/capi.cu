@@ -279,6 +279,55 @@ void damgpu_block_download_bases(const damgpu_dblock *b, uint8_t *bases)
   CUDA_CHECK(cudaMemcpy(bases - 1, blk->bases - 1, (size_t) blk->total + 1, cudaMemcpyDeviceToHost));
 }
 
+// Print_Number of the reference (DB.c:253-295): thousands separated by commas (at most three groups are
+// split off, as there), right-justified in `width` columns; width 0 = no padding
+static void print_number_w(long long num, int width, FILE *out)
+{ char digits[32], text[48];
+  const int nd = snprintf(digits, sizeof(digits), "%lld", num);
+  int groups = (nd - 1) / 3;
+  if (groups > 3) groups = 3;
+  const int lead = nd - 3 * groups;
+  int t = 0;
+  for (int i = 0; i < nd; i++)
+    { if (i >= lead && (i - lead) % 3 == 0)
+        text[t++] = ',';
+      text[t++] = digits[i];
+    }
+  text[t] = 0;
+  fprintf(out, "%*s", width, text);
+}
+
+static void print_number(long long num, FILE *out)
+{ print_number_w(num, 0, out); }
+
+// what Sort_Kmers tells the user (map.c:692-697,792-814): -v statistics and the block-size warning
+static void sort_kmers_report(const DeviceBlock *blk, const KmerIndex *idx)
+{ const long long raw = (long long) blk->total - (long long) g_par.kmer * blk->nreads;
+  const long long kmers = idx->len;
+  if (raw <= 0)                                          // no_mers (map.c:678-679): nothing is said
+    return;
+  if (g_par.verbose)
+    { printf("\n   Kmer count = ");
+      print_number(raw, stdout);
+      printf("\n   Using %.2fGb of space\n", (1. * raw) / 33554432);
+      if (g_par.suppress > 0 || blk->mask_off != nullptr)
+        { printf("   Revised kmer count = ");
+          print_number(kmers, stdout);
+          printf("\n");
+        }
+      printf("   Index occupies %.2fGb\n", (1. * kmers) / 67108864);
+      fflush(stdout);
+    }
+  if (kmers > (long long) (g_par.mem_limit / (4 * sizeof(KmerPos))))   // also with -M0, as the reference
+    { fprintf(stderr, "Warning: Block size too big, index occupies more than 1/4 of");
+      if (g_par.mem_limit == g_par.mem_physical)
+        fprintf(stderr, " physical memory (%.1fGb)\n", (1. * g_par.mem_limit) / 0x40000000ll);
+      else
+        fprintf(stderr, " desired memory allocation (%.1fGb)\n", (1. * g_par.mem_limit) / 0x40000000ll);
+      fflush(stderr);
+    }
+}
+
 damgpu_index *damgpu_index_build(const damgpu_dblock *blk)
 { need_gpu();
   if (g_par.kmer <= 1)
@@ -286,6 +335,7 @@ damgpu_index *damgpu_index_build(const damgpu_dblock *blk)
   KmerIndex *idx = sort_kmers(reinterpret_cast<const DeviceBlock *>(blk), g_par.kmer,
                               g_par.suppress, 0);
   g_sort_times[0] = idx->ms_extract; g_sort_times[1] = idx->ms_sort; g_sort_times[2] = (float) idx->npass;
+  sort_kmers_report(reinterpret_cast<const DeviceBlock *>(blk), idx);
   return reinterpret_cast<damgpu_index *>(idx);
 }
 
@@ -297,6 +347,7 @@ damgpu_index *damgpu_index_build_deferred(const damgpu_dblock *blk)
   KmerIndex *idx = sort_kmers_deferred(reinterpret_cast<const DeviceBlock *>(blk), g_par.kmer,
                                        g_par.suppress, 0);
   g_sort_times[0] = idx->ms_extract; g_sort_times[1] = idx->ms_sort; g_sort_times[2] = (float) idx->npass;
+  sort_kmers_report(reinterpret_cast<const DeviceBlock *>(blk), idx);
   return reinterpret_cast<damgpu_index *>(idx);
 }
 
@@ -378,7 +429,34 @@ void damgpu_seeds_free(damgpu_seeds *s) { free_seeds(reinterpret_cast<SeedSet *>
 
 // ---- mapper -------------------------------------------------------------------------------
 
-struct MapperH { Mapper *m; const KmerIndex *ridx; };
+struct MapperH { Mapper *m; const KmerIndex *ridx; long long tfilt = 0; };
+
+// the closing lines of Match_Filter under -v (map.c:3185-3208)
+static void match_filter_epilogue(MapperH *h, double atot, double btot, long long nhits, int start)
+{ long long nfilt = 0, none = 0, &tfilt = (h != nullptr) ? h->tfilt : none;
+  if (start) tfilt = 0;                                  // map.c:2949-2951
+  if (nhits > 0 && h != nullptr)
+    { const long long live = damgpu_mapper_num_candidates(reinterpret_cast<damgpu_mapper *>(h));
+      nfilt = live - tfilt;                              // added minus removed by this call (map.c:1684-1764)
+      tfilt = live;
+    }
+  int width = nhits <= 0 ? 1 : ((int) log10((double) nhits)) + 1;
+  width += (width - 1) / 3;
+  printf("\n     ");
+  print_number_w(nhits, width, stdout);
+  printf(" %d-mers (%e of matrix)\n     ", g_par.kmer, (1. * nhits / atot) / btot);
+  if (nfilt < 0)
+    { print_number_w(-nfilt, width, stdout);
+      printf(" candidates removed\n     ");
+    }
+  else
+    { print_number_w(nfilt, width, stdout);
+      printf(" candidates added\n     ");
+    }
+  print_number_w(tfilt, width, stdout);
+  printf(" candidates (%e of matrix)\n", (1. * tfilt / atot) / btot);
+  fflush(stdout);
+}
 
 damgpu_mapper *damgpu_mapper_new(const damgpu_dblock *reads, const damgpu_index *reads_idx)
 { need_gpu();
@@ -408,17 +486,40 @@ void damgpu_mapper_match(damgpu_mapper *mm, const damgpu_dblock *ref, const damg
   const KmerIndex *gi = reinterpret_cast<const KmerIndex *>(ref_idx);
   h->m->last_nhits = 0;
   if (h->ridx == nullptr || h->ridx->len == 0 || gi == nullptr || gi->len == 0)   // map.c:2955-2956
-    return;
+    { if (g_par.verbose)
+        match_filter_epilogue(h, (double) h->m->reads->totlen, rb != nullptr ? (double) rb->totlen : 0., 0, start);
+      return;
+    }
   SeedSet *ss = merge_join(h->ridx, h->m->reads, gi, rb, g_par.kmer, g_par.mem_limit, 0);
   h->m->last_nhits = ss->nhits; h->m->last_limit = ss->limit;
-  if (g_par.verbose)
-    { printf("\n   Capping mutual k-mer matches over %d (effectively -t%d)\n", ss->limit,
-             (int) sqrt(1. * ss->limit));
-      printf("   Hit count = %lld\n", (long long) ss->nhits);
+  if (g_par.mem_limit > 0 && ss->limit < 10)             // map.c:3029-3039 (limit <= 1 is fatal in merge_join)
+    { fprintf(stderr, "\nWarning: Sensitivity hampered by low ");
+      if (g_par.mem_limit == g_par.mem_physical)
+        fprintf(stderr, " physical memory (%.1fGb), reduce block size\n", (1. * g_par.mem_limit) / 0x40000000ll);
+      else
+        { fprintf(stderr, " memory allocation (%.1fGb),", (1. * g_par.mem_limit) / 0x40000000ll);
+          fprintf(stderr, " reduce block size or increase allocation\n");
+        }
+      fflush(stderr);
+    }
+  if (g_par.verbose)                                     // map.c:3040-3071
+    { const long long alen = h->ridx->len, blen = gi->len, nh = (long long) ss->nhits;
+      printf("\n");
+      if (g_par.mem_limit > 0)
+        printf("   Capping mutual k-mer matches over %d (effectively -t%d)\n", ss->limit,
+               (int) sqrt(1. * ss->limit));
+      printf("   Hit count = ");
+      print_number(nh, stdout);
+      if (nh >= blen)
+        printf("\n   Highwater of %.2fGb space\n", (1. * (alen + 2 * nh)) / 67108864);
+      else
+        printf("\n   Highwater of %.2fGb space\n", (1. * (alen + blen + nh)) / 67108864);
       fflush(stdout);
     }
   if (start) mapper_reset(h->m);
   chain_seeds(h->m, ss, rb->tfirst, comp, 0, g_chain_async);
+  if (g_par.verbose)
+    match_filter_epilogue(h, (double) h->m->reads->totlen, (double) rb->totlen, (long long) ss->nhits, start);
   free_seeds(ss);
 }
 
@@ -605,8 +706,7 @@ void *damgpu_Sort_Kmers(const damgpu_block *block, int *len)
 
 void damgpu_Match_Filter(const damgpu_block *ablock, const damgpu_block *bblock, void *atable,
                          int alen, void *btable, int blen, int comp, int start)
-{ (void) ablock; (void) bblock;
-  KmerIndex *ai = reinterpret_cast<KmerIndex *>(atable), *bi = reinterpret_cast<KmerIndex *>(btable);
+{ KmerIndex *ai = reinterpret_cast<KmerIndex *>(atable), *bi = reinterpret_cast<KmerIndex *>(btable);
   if (ai != nullptr && ai->block == nullptr)
     fatal("Match_Filter: the reads index was not made by damgpu_Sort_Kmers (it carries no block)");
   if (alen == 0 || blen == 0 || ai == nullptr || bi == nullptr)     // map.c:2955-2956
@@ -618,6 +718,8 @@ void damgpu_Match_Filter(const damgpu_block *ablock, const damgpu_block *bblock,
                                                                    reinterpret_cast<damgpu_index *>(ai)));
           g_mapper_key = atable;
         }
+      if (g_par.verbose)                                 // the reference still prints its closing lines
+        match_filter_epilogue(ai != nullptr ? g_mapper : nullptr, (double) ablock->totlen, (double) bblock->totlen, 0, start);
       return;
     }
   if (g_mapper == nullptr || g_mapper_key != atable)
@@ -658,7 +760,9 @@ void damgpu_Reporter(const char *aname, const damgpu_block *ablock, const char *
     if (damgpu_report_write_las(rep, 1, g_par.sort_path.c_str(), aname, bname, g_par.nthreads, g_par.spacing))
       fatal("Cannot open .las files in %s for writing", g_par.sort_path.c_str());
   if (g_par.verbose)
-    { printf("      %lld mapped segments\n", (long long) damgpu_report_records(rep, (mflag & 1) ? 0 : 1));
+    { printf("      ");                               // map.c:3289-3293
+      print_number((long long) damgpu_report_records(rep, (mflag & 1) ? 0 : 1), stdout);
+      printf(" mapped segments\n");
       fflush(stdout);
     }
   if (g_par.profile)

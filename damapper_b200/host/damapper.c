@@ -572,7 +572,16 @@ int main(int argc, char *argv[])
       }
       tick("write .las / -p track");
       if (VERBOSE)
-        { printf("      %lld mapped segments\n",(long long) damgpu_report_records(rep,(mflag & 1) ? 0 : 1));
+        { long long nseg = (long long) damgpu_report_records(rep,(mflag & 1) ? 0 : 1);
+          char digits[32];                                 /* map.c:3289-3293: commas between thousands */
+          int  nd = snprintf(digits,sizeof(digits),"%lld",nseg), d;
+          printf("      ");
+          for (d = 0; d < nd; d++)
+            { if (d > 0 && (nd-d) % 3 == 0 && nd-d <= 9)
+                putchar(',');
+              putchar(digits[d]);
+            }
+          printf(" mapped segments\n");
           fflush(stdout);
         }
       damgpu_report_free(rep);

@@ -192,3 +192,34 @@ def test_layer1_match_filter_with_an_empty_side(tmp_path):
             data = open(os.path.join(str(tmp_path), name), "rb").read()
             assert len(data) == 12 and struct.unpack("<qi", data) == (0, 100)
     api.set_options()
+
+
+@pytest.mark.parametrize("flags", [("-M16",), ("-M0", "-C", "-t20"), ("-M1", "-C", "-p", "-k16")])
+def test_verbose_statistics_match_the_reference(tmp_path, flags):
+    """-v: what Sort_Kmers, Match_Filter and Reporter tell the user (map.c:692-697,792-814,2990-3071,
+    3185-3208,3289-3293) -- k-mer counts, index sizes, the hit cap, hit counts, candidates added / removed
+    per call and in total, mapped segments, and the block-size warning on stderr -- must read exactly as the
+    reference's, from the shipped driver and from the reference's own driver linked against libdamgpu."""
+    import re
+    from damapper_b200 import dazzdb, synth
+    from oracle import run_ref
+    if not run_ref.have_ref():
+        pytest.skip("oracle/_ref/damapper is not built")
+    contigs, rb, rl = synth.make_config("C1", scale=0.05, seed=66)
+    wd = str(tmp_path)
+    dazzdb.write_db(os.path.join(wd, "ref.dam"), contigs, is_dam=True)
+    dazzdb.write_db(os.path.join(wd, "reads.db"), (rb, rl))
+
+    def said(exe):
+        r = run_ref.run_damapper(wd, "ref.dam", "reads.db", flags=("-v",) + tuple(flags), threads=4, exe=exe)
+        for f in ("prof_anno", "prof_data"):
+            if r[f]:
+                os.remove(r[f])
+        return re.sub(r"damapper\.\d+", "damapper.PID", r["stdout"]), r["stderr"]
+
+    want = said(None)
+    assert "Kmer count = " in want[0] and "candidates added" in want[0] and "mapped segments" in want[0]
+    assert said(EXE) == want
+    gpu = os.path.join(run_ref.REF_DIR, "damapper_gpu")
+    if os.access(gpu, os.X_OK):
+        assert said(gpu) == want
