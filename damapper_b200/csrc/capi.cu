@@ -710,7 +710,11 @@ void damgpu_Match_Filter(const damgpu_block *ablock, const damgpu_block *bblock,
   if (ai != nullptr && ai->block == nullptr)
     fatal("Match_Filter: the reads index was not made by damgpu_Sort_Kmers (it carries no block)");
   if (alen == 0 || blen == 0 || ai == nullptr || bi == nullptr)     // map.c:2955-2956
-    { free_index(bi);
+    { // the block sizes come from whichever side knows them (the shim of INTEGRATION.md passes no blocks)
+      const double atot = (ai != nullptr) ? (double) ai->block->totlen : (ablock != nullptr) ? (double) ablock->totlen : 0.;
+      const double btot = (bi != nullptr && bi->block != nullptr) ? (double) bi->block->totlen
+                                                                  : (bblock != nullptr) ? (double) bblock->totlen : 0.;
+      free_index(bi);
       if (ai != nullptr && (g_mapper == nullptr || g_mapper_key != atable || start))
         { // nothing to match, but the reads block is under way: Reporter writes its (empty) files
           if (g_mapper) damgpu_mapper_free(reinterpret_cast<damgpu_mapper *>(g_mapper));
@@ -719,7 +723,7 @@ void damgpu_Match_Filter(const damgpu_block *ablock, const damgpu_block *bblock,
           g_mapper_key = atable;
         }
       if (g_par.verbose)                                 // the reference still prints its closing lines
-        match_filter_epilogue(ai != nullptr ? g_mapper : nullptr, (double) ablock->totlen, (double) bblock->totlen, 0, start);
+        match_filter_epilogue(ai != nullptr ? g_mapper : nullptr, atot, btot, 0, start);
       return;
     }
   if (g_mapper == nullptr || g_mapper_key != atable)

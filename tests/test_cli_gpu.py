@@ -177,7 +177,7 @@ def test_layer1_match_filter_with_an_empty_side(tmp_path):
     empty = api.HostBlock(np.array([4], dtype=np.uint8), np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int32))
     hw = api.HostBlock(*dazzdb.load_block(contigs))
     api.set_filter_params(20, 0, 4)
-    api.set_options(sort_path=str(tmp_path))
+    api.set_options(sort_path=str(tmp_path), verbose=1)   # -v: the closing lines are printed on this path too
     spec = api.CAlignSpec(0.85, 100, (C.c_float * 4)(.25, .25, .25, .25))
     blen, alen = C.c_int(0), C.c_int(0)
     bindex = L.damgpu_Sort_Kmers(C.byref(hr.c), C.byref(blen))
