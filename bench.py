@@ -112,6 +112,24 @@ def make_workload(seed: int, reads_scale: float = 1.0):
     return contigs, rb, rl, freq
 
 
+def scratch_base():
+    """Where both arms keep their DB files and -P sort directories: BENCH_SCRATCH, else /dev/shm when it is a
+    writable tmpfs with room (what -P is for: the root volume of these boxes is ext4 mounted with `discard`,
+    on which unlinking / truncating a few MB costs milliseconds), else the default temporary directory."""
+    e = os.environ.get("BENCH_SCRATCH")
+    if e:
+        return e if os.path.isdir(e) and os.access(e, os.W_OK) else None
+    d = "/dev/shm"
+    try:
+        if os.path.isdir(d) and os.access(d, os.W_OK):
+            st = os.statvfs(d)
+            if st.f_bavail * st.f_frsize >= (4 << 30):
+                return d
+    except OSError:
+        pass
+    return None
+
+
 def host_threads():
     cores = os.cpu_count() or 1
     threads = 1
@@ -125,7 +143,8 @@ def config_of(nreads, bases, n_kmers, index):
     return {"workload": WORKLOAD, "reads_per_gpu": int(nreads), "read_bases_per_gpu": int(bases), "kmer": 20,
             "l2": "inputs larger than L2 (126 MB): the reads block is %.0f MB at one byte per base (35 MB packed), its "
                   "k-mer list %.1f GB; no flush between steps" % (bases / 1e6, 16.0 * n_kmers / 1e9),
-            "index": index}
+            "index": index,
+            "scratch": "%s for both arms (DB files, -P sort directories)" % (scratch_base() or tempfile.gettempdir())}
 
 
 # ------------------------------------------------------------------ the two command lines
@@ -147,7 +166,7 @@ def whole_process(contigs, rb, rl, device, runs=3):
         return None, None
     threads = host_threads()
     bases = int(rl.sum())
-    wd = tempfile.mkdtemp(prefix="bench_wp_")
+    wd = tempfile.mkdtemp(prefix="bench_wp_", dir=scratch_base())
     gpu_exe = os.path.join(ROOT, "damapper_b200", "damapper")
     timed = os.path.join(run_ref.REF_DIR, "damapper_timed")
     ref_w, gpu_w, core = [], [], None
@@ -196,7 +215,7 @@ def run_reference(args):
     contigs, rb, rl, freq = make_workload(seed=7)
     bases = int(rl.sum())
     n_kmers = int((rl - 19).sum())
-    wd = tempfile.mkdtemp(prefix="bench_ref_")
+    wd = tempfile.mkdtemp(prefix="bench_ref_", dir=scratch_base())
     times, core = [], None
     try:
         dazzdb.write_db(os.path.join(wd, "ref.dam"), contigs, is_dam=True)
@@ -549,7 +568,7 @@ def main():
     L.damgpu_time_kernels(0)
 
     # ---- e2e: host buffers through the map.h-shaped C ABI
-    tmpdir = tempfile.mkdtemp(prefix="bench_e2e_")
+    tmpdir = tempfile.mkdtemp(prefix="bench_e2e_", dir=scratch_base())
     sortdirs = [os.path.join(tmpdir, "s%d" % i) for i in range(2 + args.steps)]
     for d in sortdirs:
         os.makedirs(d)
