@@ -156,6 +156,11 @@ def _have_ref():
     ("C1", 0.03, 21, ("-C", "-p"), dict(do_b=1, profile=1)),
     ("C5", 0.05, 22, ("-C", "-n.8"), dict(do_b=1, best_tie=0.8)),
     ("C3", 0.003, 23, ("-p", "-n.7", "-k18"), dict(profile=1, best_tie=0.7, kmer=18)),
+    # flag sets drawn by tools/oracle_fuzz.py (92 random cases against the reference, no mismatch)
+    ("C1", 0.02, 24, ("-k14", "-n.7", "-M4", "-s126"), dict(kmer=14, best_tie=0.7, mem_limit=4 << 30, spacing=126)),
+    ("C3", 0.002, 25, ("-k28", "-C", "-n.95", "-e.9", "-t20"), dict(kmer=28, do_b=1, best_tie=0.95, ave_corr=0.9, suppress=20)),
+    ("C1", 0.02, 26, ("-e.75", "-M0", "-C", "-s200"), dict(ave_corr=0.75, mem_limit=0, do_b=1, spacing=200)),
+    ("C5", 0.04, 27, ("-k32", "-t3", "-e.7", "-s50"), dict(kmer=32, suppress=3, ave_corr=0.7, spacing=50)),
 ])
 def test_oracle_matches_reference_live(oracle_mod, cfg, scale, seed, flags, kw):
     from damapper_b200 import dazzdb, las
