@@ -25,8 +25,9 @@ struct AlignSpecD
   const int16_t *score, *table;           // device, 32768 entries each
 };
 
-// One candidate chain to extend (a warp's unit of work)
-struct AlignJob { int read, cand, first, count, status, pad; };
+// One candidate chain to extend (a warp's unit of work).  nalign / nwaves / ncells: what the duo kernel added
+// to the statistics for this job, so that k_unwind can take it back when it hands the job to the warp kernel.
+struct AlignJob { int read, cand, first, count, status; unsigned nalign, nwaves, ncells; };
 
 // One kept local alignment: A path (read vs contig) and B path (contig vs read)
 struct AlnRec

@@ -362,6 +362,10 @@ __device__ __forceinline__ void duo_control(DuoCtl &C, const AlignArgs &A)
               atomicAdd(&A.stats[4], 1ull << (16 * (C.status > 3 ? 3 : C.status - 1)));   // why (trace aid)
               C.nwaves = C.jobw0; C.nalign = C.joba0; C.ncells = C.jobc0;   // the re-run counts them
             }
+          else                                             // k_unwind may still fail the job: it then takes these back
+            { job.nalign = (unsigned) (C.nalign - C.joba0); job.nwaves = (unsigned) (C.nwaves - C.jobw0);
+              job.ncells = (unsigned) (C.ncells - C.jobc0);
+            }
           C.phase = PH_IDLE;
         }
       else

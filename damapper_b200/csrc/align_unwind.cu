@@ -186,7 +186,14 @@ k_unwind(const __grid_constant__ AlignArgs A)
 #undef POS
   if (err)
     { if (atomicExch(&A.jobs[job].status, err) == 0)
-        atomicAdd(A.nfailed, 1);
+        { atomicAdd(A.nfailed, 1);
+          // the warp kernel re-runs the job and counts its alignments, waves and cells again: what the duo
+          // kernel counted for it leaves the statistics (one thread per job gets here)
+          const AlignJob &jb = A.jobs[job];
+          atomicAdd(&A.stats[0], 0ull - (unsigned long long) jb.nalign);
+          atomicAdd(&A.stats[1], 0ull - (unsigned long long) jb.nwaves);
+          atomicAdd(&A.stats[2], 0ull - (unsigned long long) jb.ncells);
+        }
       return;
     }
   if (which == 0) { r.a[5] = tl; r.atrace = to; }

@@ -555,7 +555,8 @@ __global__ void k_fill_jobs(const int *head, const Candidate *cand, int nreads,
   if (r >= nreads) return;
   int64_t j = job_off[r];
   for (int c = head[r]; c >= 0; c = cand[c].next, j++)
-    { AlignJob jb; jb.read = r; jb.cand = c; jb.first = -1; jb.count = 0; jb.status = 0; jb.pad = 0;
+    { AlignJob jb; jb.read = r; jb.cand = c; jb.first = -1; jb.count = 0; jb.status = 0;
+      jb.nalign = jb.nwaves = jb.ncells = 0;
       jobs[j] = jb;
     }
 }

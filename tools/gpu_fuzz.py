@@ -64,7 +64,8 @@ def run_case(api, orc, cfg, scale, seed, kw, nblocks, mode):
            "M": out["a"] == o["a"], "R": out["b"] == o["b"], "prof": out["prof"] == o["prof"],
            "stats": all(out["stats"][k] == o["stats"][k] for k in ("nalign", "nwaves", "ncells")),
            "trace_check": out["stats"]["trace_fails"] == 0}
-    info = {"reads": int(len(rl)), "records": int(out["anrec"] + out["bnrec"]), "bytes": len(out["a"]) + len(out["b"]),
+    stat_pair = {k: (int(out["stats"][k]), int(o["stats"][k])) for k in ("nalign", "nwaves", "ncells")}
+    info = {"stats_gpu_oracle": stat_pair, "reads": int(len(rl)), "records": int(out["anrec"] + out["bnrec"]), "bytes": len(out["a"]) + len(out["b"]),
             "overflow_jobs": int(out["stats"].get("overflow_jobs", 0)), "deferred": bool(out["deferred"]),
             "limit": int(out["limit"])}
     return res, info
@@ -74,6 +75,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=60.)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--replay", default=None, help="a gpu_fuzz.jsonl: re-run its failed cases first")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "gpu_fuzz.jsonl"))
     args = ap.parse_args()
     from damapper_b200 import api
@@ -84,9 +86,15 @@ def main():
     t_end = time.time() + args.seconds
     n = bad = 0
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    replay = []
+    if args.replay and os.path.exists(args.replay):
+        for l in open(args.replay):
+            d = json.loads(l)
+            if not d.get("ok", True):
+                replay.append((d["cfg"], d["scale"], d["seed"], d["kw"], d["ref_blocks"], d["reads_index"]))
     with open(args.out, "a") as log:
-        while time.time() < t_end:
-            cfg, scale, seed, kw, nblocks, mode = draw(rng)
+        while replay or time.time() < t_end:
+            cfg, scale, seed, kw, nblocks, mode = replay.pop(0) if replay else draw(rng)
             case = {"cfg": cfg, "scale": round(scale, 5), "seed": seed, "kw": kw, "ref_blocks": nblocks, "reads_index": mode}
             print("case", json.dumps(case), flush=True)
             t0 = time.time()
