@@ -853,11 +853,11 @@ k_align(AlignArgs A)
     wm.tbuf = A.tscratch + (size_t) gw * 4 * wm.tcap;
   }
 
-  WaveStats st = { 0, 0, 0, 0 };
   const int hithr = 3 * A.kmer;                          // HITMIN*Kmer, map.c:2419
 
   while (true)
-    { int j = 0;
+    { WaveStats st = { 0, 0, 0, 0 };                     // of this job: counted only when the job succeeds
+      int j = 0;
       if (lane == 0) j = atomicAdd(A.job_counter, 1);
       j = __shfl_sync(0xffffffffu, j, 0);
       if (j >= A.njobs) break;
@@ -931,12 +931,12 @@ k_align(AlignArgs A)
           job.count = (status == 0) ? count : 0;
           job.status = status;
           if (status != 0)
-            atomicAdd(A.nfailed, 1);
+            atomicAdd(A.nfailed, 1);                     // re-run whole by the next round, which counts it
+          else
+            { atomicAdd(&A.stats[0], st.nalign); atomicAdd(&A.stats[1], st.nwaves);
+              atomicAdd(&A.stats[2], st.ncells); atomicAdd(&A.stats[3], st.empty);
+            }
         }
-    }
-  if (lane == 0)
-    { atomicAdd(&A.stats[0], st.nalign); atomicAdd(&A.stats[1], st.nwaves);
-      atomicAdd(&A.stats[2], st.ncells); atomicAdd(&A.stats[3], st.empty);
     }
 }
 
