@@ -201,3 +201,32 @@ def test_stream_db_writer_equals_write_db(tmp_path):
     w.append(np.concatenate(contigs), [c.size for c in contigs]); w.close()
     for f in ("reads.db", ".reads.idx", ".reads.bps", "ref.dam", ".ref.idx", ".ref.bps"):
         assert filecmp.cmp(os.path.join(d1, f), os.path.join(d2, f), shallow=False), f
+
+
+@pytest.mark.skipif(not _have_ref(), reason="oracle/_ref (compiled reference) not present")
+@pytest.mark.parametrize("cfg,scale,seed,flags,kw", [
+    ("C5", 0.04, 81, ("-k28", "-C", "-p", "-n.9", "-e.8", "-s80", "-t3"),
+     dict(kmer=28, do_b=1, profile=1, best_tie=0.9, ave_corr=0.8, spacing=80, suppress=3)),
+    ("C3", 0.002, 82, ("-C", "-p", "-n.7", "-M0"), dict(do_b=1, profile=1, best_tie=0.7, mem_limit=0)),
+])
+def test_oracle_masks_match_reference_live(oracle_mod, cfg, scale, seed, flags, kw):
+    """-mdust -mtan with other flags on top (-t run suppression after masking, -k, -s, -M0), against a live
+    run of the reference; drawn by `tools/oracle_fuzz.py <n> <seed> masks` (30 cases, no mismatch)."""
+    from damapper_b200 import dazzdb, las
+    from oracle import make_golden as mg, run_ref
+    orc = oracle_mod
+    contigs, rb, rl, rd, rf, rc = make_case(cfg, scale, seed)
+    wd = tempfile.mkdtemp(prefix="orc_ref_")
+    try:
+        gd, rm = mg.write_mask_case(wd, contigs, rb, rl, seed)
+        r = run_ref.run_damapper(wd, "ref.dam", "reads.db", flags=tuple(flags) + ("-mdust", "-mtan"), threads=1)
+        ref_a = las.canonical_stream(r["m_files"])
+        ref_b = las.canonical_stream(r["r_files"]) if r["r_files"] else b""
+        ref_p = open(r["prof_data"], "rb").read() if r["prof_data"] else b""
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+    gc = dazzdb.mirror_masks(gd[0], gd[1], rf[2])
+    out = orc.map_block(orc.HostBlock(*rd, mask=rm), [(orc.HostBlock(*rf, mask=gd), orc.HostBlock(*rc, mask=gc))],
+                        orc.HostBlock(*rf), freq=base_freq(contigs), **kw)
+    assert len(ref_a) > 1000
+    assert out["a"] == ref_a and out["b"] == ref_b and out["prof"] == ref_p

@@ -3,7 +3,7 @@ CPU only: random flag sets, seeds and workload shapes at sizes that run in secon
 case and a summary; a mismatch is a finding about the ORACLE (test infrastructure), to be fixed before
 any GPU parity claim that rests on it.
 
-    python tools/oracle_fuzz.py [ncases] [seed]
+    python tools/oracle_fuzz.py [ncases] [seed] [masks]
 """
 import os
 import shutil
@@ -23,6 +23,7 @@ def main():
     from oracle import oracle as orc, run_ref
     ncases = int(sys.argv[1]) if len(sys.argv) > 1 else 20
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+    masked = len(sys.argv) > 3 and sys.argv[3] == "masks"
     bad = 0
     for it in range(ncases):
         cfg = rng.choice(["C1", "C1", "C5", "C3"])
@@ -54,10 +55,18 @@ def main():
         else:
             flags.append("-M16"); kw["mem_limit"] = 16 << 30
         contigs, rb, rl, rd, rf, rc = make_case(cfg, scale, seed)
+        masks = masked and rng.random() < 0.6               # -mdust -mtan: random interval tracks on both DBs
+        rm = gd = gc = None
         wd = tempfile.mkdtemp(prefix="orc_fuzz_")
         try:
-            dazzdb.write_db(os.path.join(wd, "ref.dam"), contigs, is_dam=True)
-            dazzdb.write_db(os.path.join(wd, "reads.db"), (rb, rl))
+            if masks:
+                from oracle import make_golden as mg
+                gd, rm = mg.write_mask_case(wd, contigs, rb, rl, seed)
+                gc = dazzdb.mirror_masks(gd[0], gd[1], rf[2])
+                flags += ["-mdust", "-mtan"]
+            else:
+                dazzdb.write_db(os.path.join(wd, "ref.dam"), contigs, is_dam=True)
+                dazzdb.write_db(os.path.join(wd, "reads.db"), (rb, rl))
             # -p on repeat-rich input: the reference's threaded run is not deterministic
             r = run_ref.run_damapper(wd, "ref.dam", "reads.db", flags=flags, threads=1 if "-p" in flags else 2)
             ref_a = las.canonical_stream(r["m_files"])
@@ -65,8 +74,12 @@ def main():
             ref_p = open(r["prof_data"], "rb").read() if r["prof_data"] else b""
         finally:
             shutil.rmtree(wd, ignore_errors=True)
-        out = orc.map_block(orc.HostBlock(*rd), [(orc.HostBlock(*rf), orc.HostBlock(*rc))],
-                            orc.HostBlock(*rf), freq=base_freq(contigs), **kw)
+        if masks:
+            out = orc.map_block(orc.HostBlock(*rd, mask=rm), [(orc.HostBlock(*rf, mask=gd), orc.HostBlock(*rc, mask=gc))],
+                                orc.HostBlock(*rf), freq=base_freq(contigs), **kw)
+        else:
+            out = orc.map_block(orc.HostBlock(*rd), [(orc.HostBlock(*rf), orc.HostBlock(*rc))],
+                                orc.HostBlock(*rf), freq=base_freq(contigs), **kw)
         ok = (out["a"] == ref_a, out["b"] == ref_b, out["prof"] == ref_p)
         if not all(ok):
             bad += 1
