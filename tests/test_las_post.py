@@ -17,8 +17,8 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 @pytest.fixture(scope="module")
 def post(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("laspost") / "las_post.so")
-    subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", so,
-                           os.path.join(ROOT, "damapper_b200", "host", "las_post.c")])
+    subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC"] + os.environ.get("DAMGPU_TEST_CFLAGS", "").split() +
+                          ["-o", so, os.path.join(ROOT, "damapper_b200", "host", "las_post.c")])
     L = C.CDLL(so)
     L.las_sort_cat.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int]
     L.las_sort_cat.restype = C.c_int
