@@ -414,6 +414,10 @@ int main(int argc, char *argv[])
     }
 
   { char *newpath = (char *) malloc(strlen(SORT_PATH)+30);   /* damapper.c:806-817 */
+    if (newpath == NULL)
+      { fprintf(stderr,"%s: Out of memory (Allocating sort path)\n",Prog_Name);
+        exit (1);
+      }
     sprintf(newpath,"%s/damapper.%d",SORT_PATH,getpid());
     if (mkdir(newpath,S_IRWXU) != 0)
       { fprintf(stderr,"%s: Could not create directory %s\n",Prog_Name,newpath);
@@ -465,10 +469,15 @@ int main(int argc, char *argv[])
           }
       if (bblock.part > 0)
         { broot = (char *) malloc(strlen(bblock.root)+20);
-          sprintf(broot,"%s.%d",bblock.root,bblock.part);
+          if (broot != NULL)
+            sprintf(broot,"%s.%d",bblock.root,bblock.part);
         }
       else
         broot = strdup(bblock.root);
+      if (broot == NULL)
+        { fprintf(stderr,"%s: Out of memory (Allocating block name)\n",Prog_Name);
+          Clean_Exit(1);
+        }
       dazz_view(&bblock,&bview);
       tick("load reads block");
       if (VERBOSE)
