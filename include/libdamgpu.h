@@ -59,7 +59,7 @@ typedef struct {
 
 /* The globals map.h:16-23 declares extern and damapper.c:58-65 defines. */
 typedef struct {
-  int32_t     verbose;      /* VERBOSE  */
+  int32_t     verbose;      /* VERBOSE: the core's statistics on stdout, as map.c:692-697,792-814,2990-3071,3185-3208 */
   int32_t     profile;      /* PROFILE  (-p) */
   int32_t     spacing;      /* SPACING  (-s) */
   double      best_tie;     /* BEST_TIE (-n) */
