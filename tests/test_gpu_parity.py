@@ -610,3 +610,19 @@ def test_host_driver_multiblock_reference_cache(api, tmp_path):
     assert all(len(v[2]) > 0 for v in cached.values())
     assert cached == plain
 
+
+
+def test_output_pools_grow_over_several_overflow_rounds(api, oracle_mod):
+    """-e.9 on 15 % reads ends alignments early: a candidate chain yields many short alignments, far more than the
+    two records per job the output pools are first sized for.  The jobs that find the pools full are re-run by the
+    warp kernel with doubled pools, and again, until they fit (report.cu overflow rounds).  A case drawn by
+    tools/gpu_fuzz.py (k=14, two reference blocks, -C -p): candidates, Jump lists, both record families and the
+    -p track as the oracle's."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gpu_fuzz
+    res, info = gpu_fuzz.run_case(api, oracle_mod, "C2", 0.03769, 723234,
+                                  dict(kmer=14, do_b=1, profile=1, ave_corr=0.9), 2, "always")
+    assert info["overflow_jobs"] > 100 and info["records"] > 1000
+    for key in ("candidates", "jumps", "M", "R", "prof", "trace_check"):
+        assert res[key], key
