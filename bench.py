@@ -7,9 +7,10 @@ A step = the whole hot path for one reads block: Sort_Kmers(reads), then per ref
 Sort_Kmers + Match_Filter for both orientations, then Reporter (chain extension, selection,
 records copied back).  N > 1 (torchrun, one rank per GPU): every rank maps its own reads
 block (weak scaling); reads need no collective.  The reference index (2 x 74 MB here) is built by
-every rank for itself by default: at this size the local build (0.3 ms) is cheaper than an NCCL
-broadcast with its length exchange (measured 0.7 ms per step in round 1); --index broadcast
-builds it on rank 0 and broadcasts it (the form for chromosome-scale references).
+every rank for itself: measured on 2 x B200, the local build is never slower than an NCCL broadcast
+or a sharded build + all-gather, at 4.6 Mbp and at 250 Mbp; --index broadcast
+keeps the NCCL path measurable.  Both arms keep DB files and -P sort directories in one scratch
+directory (config.scratch: /dev/shm when it is a tmpfs with room).
 
   value  inputs resident in HBM when the timed region starts (blocks already uploaded)
   e2e    through the reference-facing C ABI (the four map.h calls) with host buffers in pinned
