@@ -119,3 +119,28 @@ def test_builtin_sort_leaves_the_final_files(mock_exe, tmp_path):
         ref_recs = las.stream_records(want[2][fam], 100)
         assert len(recs) == len(ref_recs) >= 30
         assert sorted(blob(r) for r in recs) == sorted(blob(r) for r in ref_recs), name
+
+
+def test_reads_shorter_than_k_and_plain_db(mock_exe, tmp_path):
+    """damapper.c:403-410: a block holding a read shorter than k stops the run with the reference's message; an
+    unsplit reads DB (no block suffix) is mapped whole."""
+    import numpy as np
+    from damapper_b200 import dazzdb, synth
+    from oracle import run_ref
+    wd = str(tmp_path)
+    contigs, rb, rl = synth.make_config("C1", scale=0.03, seed=67)
+    dazzdb.write_db(os.path.join(wd, "ref.dam"), contigs, is_dam=True)
+    dazzdb.write_db(os.path.join(wd, "reads.db"), (rb, rl))
+    r = run_ref.run_damapper(wd, "ref.dam", "reads.db", flags=("-M16",), threads=4, exe=mock_exe)
+    want = run_ref.run_damapper(wd, "ref.dam", "reads.db", flags=("-M16",), threads=4)
+    from damapper_b200 import las
+    assert las.canonical_stream(r["m_files"]) == las.canonical_stream(want["m_files"])
+    short = np.concatenate([rb, np.zeros(12, dtype=np.uint8)])
+    dazzdb.write_db(os.path.join(wd, "bad.db"), (short, np.concatenate([rl, [12]]).astype(rl.dtype)))
+    os.makedirs(os.path.join(wd, "tmps"))
+    cmd = ["-T4", "-P" + os.path.join(wd, "tmps"), "ref.dam", "bad.db"]
+    q = subprocess.run([mock_exe] + cmd, cwd=wd, capture_output=True, text=True)
+    w = subprocess.run([run_ref.REF_BIN] + cmd, cwd=wd, capture_output=True, text=True)
+    assert q.returncode == w.returncode == 1
+    assert "contains reads < 20bp long" in q.stderr and "contains reads < 20bp long" in w.stderr
+    assert glob.glob(os.path.join(wd, "tmps", "damapper.*")) == []
